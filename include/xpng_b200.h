@@ -1,0 +1,80 @@
+/*
+ * xpng_b200.h — batch / in-memory C ABI of the B200-native xPNG codec.
+ *
+ * The reference (alantudyk/xPNG) exposes only a file-at-a-time API (xpng.h:12-20, re-declared in
+ * include/xpng.h and implemented on top of this interface).  This header adds what a GPU needs to
+ * be measured and sharded: N images in, N `.xpng` byte strings out (and back), with the pixels and
+ * the compressed bytes in HOST or DEVICE memory.  Plain C types only; no CUDA or torch types.
+ *
+ * Reference interfaces replaced:
+ *   xpngb_encode  <->  xpng_store_T   (libxpng.c:723-789) minus the fopen/fwrite
+ *   xpngb_decode  <->  xpng_load_T    (libxpng.c:963-997) minus the f_read/malloc
+ *   xpngb_peek    <->  header parse   (libxpng.c:969-973)
+ * All functions return 0 on success and non-zero on failure (the reference's _Bool convention).
+ */
+#ifndef XPNG_B200_H
+#define XPNG_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct xpngb_ctx xpngb_ctx;
+
+/* One image of a batch.  `offset` is the byte offset of its pixels (interleaved 8-bit RGB or RGBA,
+ * row-major, w*h*(3+A) bytes) inside the pixel buffer; it must be a multiple of 16. */
+typedef struct xpngb_image {
+    uint64_t w, h;
+    uint64_t offset;
+    uint32_t A;        /* 1 = RGBA */
+    uint32_t mode;     /* out (encode): level actually written (1, 2, 7); out (decode): level found */
+} xpngb_image;
+
+/* Create / destroy a codec context bound to CUDA device `device`.  Fails (non-zero) when no usable
+ * CUDA device exists: there is no CPU fallback. */
+int xpngb_create(xpngb_ctx **ctx, int device);
+void xpngb_destroy(xpngb_ctx *ctx);
+const char *xpngb_last_error(const xpngb_ctx *ctx);
+
+/* Upper bound of the output bytes xpngb_encode needs for these images (16-byte padded files). */
+uint64_t xpngb_encode_bound(const xpngb_image *imgs, uint32_t n);
+
+/* Encode n images at `level` (1, 2 or 7).
+ *   pixels / pixels_on_device : base of the pixel buffer (host or device memory), `pixels_size` bytes
+ *   out / out_on_device       : receives the .xpng files, file i at out_offsets[i], out_sizes[i] bytes
+ * imgs[i].A and imgs[i].mode are updated to what the file header says (alpha may be stripped by the
+ * normalisation of libxpng.c:688-721; a level may fall back to 7). */
+int xpngb_encode(xpngb_ctx *ctx, int level, xpngb_image *imgs, uint32_t n,
+                 const void *pixels, uint64_t pixels_size, int pixels_on_device,
+                 void *out, uint64_t out_cap, int out_on_device,
+                 uint64_t *out_offsets, uint64_t *out_sizes);
+
+/* Read w, h, A, mode from the first 8 bytes of a .xpng file held in host memory. */
+int xpngb_peek(const void *file, uint64_t size, xpngb_image *img);
+
+/* Decode n files.  imgs[i] must carry w, h, A (from xpngb_peek) and `offset` = where image i's
+ * pixels go inside `pixels` (multiple of 16).  files / pixels may live on host or device. */
+int xpngb_decode(xpngb_ctx *ctx, xpngb_image *imgs, uint32_t n,
+                 const void *files, uint64_t files_size, int files_on_device,
+                 const uint64_t *file_offsets, const uint64_t *file_sizes,
+                 void *pixels, uint64_t pixels_cap, int pixels_on_device);
+
+/* Device time of the kernels of the last encode/decode call on this context, in milliseconds
+ * (CUDA events on the context's stream; excludes host<->device copies). */
+float xpngb_last_kernel_ms(const xpngb_ctx *ctx);
+/* Number of kernel launches issued by the last call. */
+uint32_t xpngb_last_launches(const xpngb_ctx *ctx);
+/* The CUDA stream (cudaStream_t as void*) the context launches on. */
+void *xpngb_stream(const xpngb_ctx *ctx);
+
+/* Reversible YCoCg-R lifting of n RGB triples on the device (Tell_Me_Why/YCoCg-R.c:22,:31): a side
+ * component, NOT part of the .xpng bit stream.  rgb: 3*n bytes; ycc: 3*n int16 (Y, Co, Cg). */
+int xpngb_ycocg_forward(xpngb_ctx *ctx, const uint8_t *rgb_host, int16_t *ycc_host, uint64_t n);
+int xpngb_ycocg_inverse(xpngb_ctx *ctx, const int16_t *ycc_host, uint8_t *rgb_host, uint64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,558 @@
+// api.cu — host orchestration and the C ABI (include/xpng_b200.h) of the B200 xPNG codec.
+// Everything here is plumbing: tile tables (libxpng.c:51-83), scratch layout, kernel launches on one
+// stream, host<->device copies.  All codec arithmetic lives in the kernels.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/xpng_b200.h"
+#include "common.cuh"
+#include "enc_front.cuh"
+#include "enc_back.cuh"
+#include "dec_m1.cuh"
+#include "misc.cuh"
+
+using namespace xpb;
+
+struct DevBuf { void* p = nullptr; size_t cap = 0; };
+struct PinBuf { void* p = nullptr; size_t cap = 0; };
+
+struct xpngb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    char err[512] = { 0 };
+    float last_ms = 0.f;
+    uint32_t launches = 0;
+    uint64_t max_chunk_px = 1ull << 30;
+    // device scratch
+    DevBuf pixels, norm, files, arena, tiles, imgs, seg_tile, costs, hist, seginfo, place, vplace, vcnt, sym_area,
+        bits_area, alpha, streams, blocks, state, outs, flags, skip, dimgs, dtiles, plane, nlseq, rowcnt, rowbits,
+        rows, edge, errflag, hdr, offs, m2a, m2b;
+    PinBuf pin_a, pin_b;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            snprintf(ctx->err, sizeof ctx->err, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            return 1;                                                                              \
+        }                                                                                          \
+    } while (0)
+#define FAIL(...)                                                \
+    do {                                                         \
+        snprintf(ctx->err, sizeof ctx->err, __VA_ARGS__);        \
+        return 1;                                                \
+    } while (0)
+#define LAUNCH(kernel, grid, block, smem, ...)                   \
+    do {                                                         \
+        kernel<<<grid, block, smem, ctx->stream>>>(__VA_ARGS__); \
+        ctx->launches++;                                         \
+        CK(cudaGetLastError());                                  \
+    } while (0)
+
+static int ensure(xpngb_ctx* ctx, DevBuf& b, size_t n) {
+    n += 64;   // tail slack for vector over-reads
+    if (b.cap >= n) return 0;
+    if (b.p) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = n + n / 8;
+    CK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+static int ensure_pin(xpngb_ctx* ctx, PinBuf& b, size_t n) {
+    if (b.cap >= n) return 0;
+    if (b.p) { CK(cudaStreamSynchronize(ctx->stream)); CK(cudaFreeHost(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = n + n / 8 + 4096;
+    CK(cudaMallocHost(&b.p, want));
+    b.cap = want;
+    return 0;
+}
+#define ENSURE(buf, n) do { if (ensure(ctx, ctx->buf, (n))) return 1; } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Tile grid (libxpng.c:51-83): base tile 444x444 (or full width/height when the image is thinner),
+// the remainder of each axis goes to the first tile, or to the first two when it exceeds half a tile.
+// ------------------------------------------------------------------------------------------------
+static uint64_t axis_cut(uint64_t extent, uint64_t base, uint64_t* first, uint64_t* second) {
+    uint64_t n = extent / base, rem = extent % base;
+    *first = base + rem; *second = base;
+    if (rem > base / 2) { n++; *second = (base + rem) / 2; *first = *second + ((base + rem) & 1); }
+    return n;
+}
+
+struct Plan {
+    std::vector<ImageDesc> imgs;
+    std::vector<TileDesc> tiles;
+    std::vector<uint32_t> seg_tile;
+    uint64_t px_total = 0, row_total = 0, str_total = 0, blk_total = 0;
+    bool any_rgba = false;
+};
+
+// Appends the tiles of one image.  base = absolute device address of its pixels.
+static void plan_image(Plan& P, uint64_t base, uint64_t W, uint64_t H, uint32_t pxsz, uint32_t mode, int sfac, int bfac) {
+    ImageDesc I{};
+    I.px_off = base; I.raw_size = W * H * pxsz; I.w = (uint32_t)W; I.h = (uint32_t)H; I.pxsz = pxsz;
+    I.tile0 = (uint32_t)P.tiles.size(); I.mode = mode;
+    uint64_t nw = 1, nh = 1, w0 = W, w1 = W, wb = W, h0 = H, h1 = H, hb = H;
+    if (W * H > TILE_AREA) {
+        if (W < 444) { wb = W; hb = TILE_AREA / W; }
+        else if (H < 444) { hb = H; wb = TILE_AREA / H; }
+        else wb = hb = 444;
+        nw = axis_cut(W, wb, &w0, &w1);
+        nh = axis_cut(H, hb, &h0, &h1);
+    }
+    const uint32_t img = (uint32_t)P.imgs.size();
+    uint64_t y = 0; uint32_t tix = 0;
+    for (uint64_t i = 0; i < nh; i++) {
+        const uint64_t th = i == 0 ? h0 : (i == 1 ? h1 : hb);
+        uint64_t x = 0;
+        for (uint64_t j = 0; j < nw; j++) {
+            const uint64_t tw = j == 0 ? w0 : (j == 1 ? w1 : wb);
+            TileDesc t{};
+            t.src_off = base + (y * W + x) * pxsz;
+            t.px_off = P.px_total; t.row_off = P.row_total;
+            t.w = (uint32_t)tw; t.h = (uint32_t)th; t.bpr = (uint32_t)(W * pxsz); t.npx = (uint32_t)(tw * th);
+            t.img = img; t.seg0 = (uint32_t)P.seg_tile.size(); t.nseg = (t.npx + SEG - 1) / SEG; t.pxsz = pxsz;
+            t.x0 = (uint32_t)x; t.y0 = (uint32_t)y; t.tix = tix++;
+            const uint64_t slice = ((uint64_t)t.npx + 15) / 16 * 16 + 256;
+            t.str_off = P.str_total; t.blk_off = P.blk_total;
+            P.px_total += slice; P.row_total += th;
+            P.str_total += slice * sfac; P.blk_total += slice * bfac + 8192;
+            for (uint32_t s = 0; s < t.nseg; s++) P.seg_tile.push_back((uint32_t)P.tiles.size());
+            P.tiles.push_back(t);
+            x += tw;
+        }
+        y += th;
+    }
+    I.ntiles = (uint32_t)P.tiles.size() - I.tile0;
+    if (pxsz == 4) P.any_rgba = true;
+    P.imgs.push_back(I);
+}
+
+static int upload_plan(xpngb_ctx* ctx, const Plan& P) {
+    const size_t nb_t = P.tiles.size() * sizeof(TileDesc), nb_i = P.imgs.size() * sizeof(ImageDesc), nb_s = P.seg_tile.size() * 4;
+    ENSURE(tiles, nb_t); ENSURE(imgs, nb_i); ENSURE(seg_tile, nb_s);
+    if (ensure_pin(ctx, ctx->pin_a, nb_t + nb_i + nb_s)) return 1;
+    uint8_t* h = (uint8_t*)ctx->pin_a.p;
+    memcpy(h, P.tiles.data(), nb_t); memcpy(h + nb_t, P.imgs.data(), nb_i); memcpy(h + nb_t + nb_i, P.seg_tile.data(), nb_s);
+    CK(cudaMemcpyAsync(ctx->tiles.p, h, nb_t, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->imgs.p, h + nb_t, nb_i, cudaMemcpyHostToDevice, ctx->stream));
+    if (nb_s) CK(cudaMemcpyAsync(ctx->seg_tile.p, h + nb_t + nb_i, nb_s, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Level 2 host side
+// ------------------------------------------------------------------------------------------------
+static void m2_set_attributes() {}
+static int m2_encode_tiles(xpngb_ctx* ctx, const Plan&, uint32_t, uint32_t) { FAIL("level 2 encode not implemented yet"); }
+static int m2_assemble(xpngb_ctx* ctx, const AssembleArgs&, uint32_t) { FAIL("level 2 encode not implemented yet"); }
+static int m2_decode_tiles(xpngb_ctx* ctx, const Plan&, const DecImage*, DecTile*, const uint8_t*, uint32_t) { FAIL("level 2 decode not implemented yet"); }
+
+// ------------------------------------------------------------------------------------------------
+// Context
+// ------------------------------------------------------------------------------------------------
+extern "C" int xpngb_create(xpngb_ctx** out, int device) {
+    if (!out) return 1;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return 1;
+    if (cudaSetDevice(device) != cudaSuccess) return 1;
+    xpngb_ctx* ctx = new xpngb_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) { delete ctx; return 1; }
+    if (const char* e = getenv("XPNGB_CHUNK_MPIX")) { const long v = atol(e); if (v > 0) ctx->max_chunk_px = (uint64_t)v << 20; }
+    { auto k_big = k_rans_v2<256, 32>; cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 16); }
+    m2_set_attributes();
+    *out = ctx;
+    return 0;
+}
+
+extern "C" void xpngb_destroy(xpngb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* all[] = { &ctx->pixels, &ctx->norm, &ctx->files, &ctx->arena, &ctx->tiles, &ctx->imgs, &ctx->seg_tile, &ctx->costs,
+                      &ctx->hist, &ctx->seginfo, &ctx->place, &ctx->vplace, &ctx->vcnt, &ctx->sym_area, &ctx->bits_area, &ctx->alpha,
+                      &ctx->streams, &ctx->blocks, &ctx->state, &ctx->outs, &ctx->flags, &ctx->skip, &ctx->dimgs, &ctx->dtiles,
+                      &ctx->plane, &ctx->nlseq, &ctx->rowcnt, &ctx->rowbits, &ctx->rows, &ctx->edge, &ctx->errflag, &ctx->hdr,
+                      &ctx->offs, &ctx->m2a, &ctx->m2b };
+    for (DevBuf* b : all) if (b->p) cudaFree(b->p);
+    if (ctx->pin_a.p) cudaFreeHost(ctx->pin_a.p);
+    if (ctx->pin_b.p) cudaFreeHost(ctx->pin_b.p);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* xpngb_last_error(const xpngb_ctx* ctx) { return ctx ? ctx->err : "no context"; }
+extern "C" float xpngb_last_kernel_ms(const xpngb_ctx* ctx) { return ctx ? ctx->last_ms : 0.f; }
+extern "C" uint32_t xpngb_last_launches(const xpngb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void* xpngb_stream(const xpngb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+extern "C" uint64_t xpngb_encode_bound(const xpngb_image* imgs, uint32_t n) {
+    uint64_t t = 0;
+    for (uint32_t i = 0; i < n; i++) t += (8 + imgs[i].w * imgs[i].h * (3 + (imgs[i].A ? 1 : 0)) + 15) & ~15ull;
+    return t;
+}
+
+extern "C" int xpngb_peek(const void* file, uint64_t size, xpngb_image* img) {
+    if (!file || !img || size < 8) return 1;
+    uint32_t h[2]; memcpy(h, file, 8);
+    img->w = (h[0] & 0xFFFFFFu) + 1; img->h = (h[1] & 0xFFFFFFu) + 1; img->A = (h[1] >> 24) & 1; img->mode = h[0] >> 24;
+    return !(img->mode == 1 || img->mode == 2 || img->mode == 7);   // libxpng.c:972
+}
+
+// ------------------------------------------------------------------------------------------------
+// Encode
+// ------------------------------------------------------------------------------------------------
+static int encode_chunk(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32_t n, const uint8_t* dpix, uint8_t* dout,
+                        uint64_t out_base, uint64_t out_cap, uint64_t* out_offsets, uint64_t* out_sizes, uint64_t* used) {
+    // ---- normalisation / whole-image scans (one sync, only when needed)
+    bool any_rgba = false;
+    for (uint32_t i = 0; i < n; i++) any_rgba |= imgs[i].A != 0;
+    std::vector<uint32_t> flags(n, 0);
+    std::vector<uint64_t> addr(n);
+    std::vector<uint32_t> pxsz(n);
+    for (uint32_t i = 0; i < n; i++) { addr[i] = (uint64_t)(dpix + imgs[i].offset); pxsz[i] = imgs[i].A ? 4 : 3; }
+    if (any_rgba || level == 2) {
+        Plan S;   // only the image table is used
+        for (uint32_t i = 0; i < n; i++) {
+            ImageDesc I{}; I.px_off = addr[i]; I.w = (uint32_t)imgs[i].w; I.h = (uint32_t)imgs[i].h; I.pxsz = pxsz[i];
+            I.raw_size = imgs[i].w * imgs[i].h * pxsz[i];
+            S.imgs.push_back(I);
+        }
+        const size_t nb = n * sizeof(ImageDesc);
+        ENSURE(imgs, nb); ENSURE(flags, n * 4);
+        if (ensure_pin(ctx, ctx->pin_a, nb)) return 1;
+        memcpy(ctx->pin_a.p, S.imgs.data(), nb);
+        CK(cudaMemcpyAsync(ctx->imgs.p, ctx->pin_a.p, nb, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ctx->flags.p, 0, n * 4, ctx->stream));
+        LAUNCH(k_image_scan, dim3(64, n), 256, 0, (const ImageDesc*)ctx->imgs.p, (uint32_t*)ctx->flags.p);
+        CK(cudaMemcpyAsync(flags.data(), ctx->flags.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        // apply normalisation (libxpng.c:688-721)
+        uint64_t need = 0;
+        for (uint32_t i = 0; i < n; i++) if (imgs[i].A && ((flags[i] & SCAN_DIRTY) || !(flags[i] & SCAN_TRANSLUCENT)))
+            need += (imgs[i].w * imgs[i].h * 4 + 15) & ~15ull;
+        if (need) {
+            ENSURE(norm, need);
+            uint64_t o = 0;
+            for (uint32_t i = 0; i < n; i++) {
+                if (!imgs[i].A) continue;
+                const uint64_t npx = imgs[i].w * imgs[i].h;
+                uint8_t* dst = (uint8_t*)ctx->norm.p + o;
+                const unsigned grid = (unsigned)((npx + 1023) / 1024 > 1184 ? 1184 : (npx + 1023) / 1024);
+                if (flags[i] & SCAN_DIRTY) LAUNCH(k_alpha_zero, grid, 256, 0, (const uint32_t*)addr[i], (uint32_t*)dst, npx);
+                else if (!(flags[i] & SCAN_TRANSLUCENT)) { LAUNCH(k_alpha_strip, grid, 256, 0, (const uint32_t*)addr[i], dst, npx); pxsz[i] = 3; }
+                else continue;
+                addr[i] = (uint64_t)dst; o += (npx * 4 + 15) & ~15ull;
+            }
+        }
+    }
+    // ---- effective level per image (libxpng.c:735, :741-755)
+    std::vector<uint32_t> mode(n);
+    bool any1 = false, any2 = false;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint64_t s = imgs[i].w * imgs[i].h * pxsz[i];
+        uint32_t m = (uint32_t)level;
+        if (s <= 4) m = 7;
+        if (m == 2 && !(flags[i] & SCAN_NOT_SINGLE)) m = 2 | 0x100;
+        else if (m == 2 && pxsz[i] == 4) m = 1;
+        if ((m == 1) && pxsz[i] == 4 && (imgs[i].w < 4 || imgs[i].h < 4))
+            FAIL("image %u: RGBA tiles thinner than 4 pixels are not encodable at level 1/2 (the reference crashes here)", i);
+        mode[i] = m; any1 |= m == 1; any2 |= m == 2;
+    }
+    if (any1 && any2) {
+        // level 2 with some images that keep alpha (coded at level 1, libxpng.c:755): encode each run of one family on its own
+        uint64_t base = out_base; uint32_t a = 0;
+        while (a < n) {
+            const bool fam1 = mode[a] == 1; uint32_t b = a;
+            while (b < n && (mode[b] == 1) == fam1) b++;
+            if (encode_chunk(ctx, fam1 ? 1 : 2, imgs + a, b - a, dpix, dout, base, out_cap, out_offsets + a, out_sizes + a, &base)) return 1;
+            a = b;
+        }
+        *used = base;
+        return 0;
+    }
+    // ---- plan
+    Plan P;
+    const int sfac = any2 ? 4 : 1, bfac = any2 ? 8 : 4;
+    for (uint32_t i = 0; i < n; i++) plan_image(P, addr[i], imgs[i].w, imgs[i].h, pxsz[i], mode[i], sfac, bfac);
+    const uint32_t ntiles = (uint32_t)P.tiles.size(), nseg = (uint32_t)P.seg_tile.size();
+    if (upload_plan(ctx, P)) return 1;
+    ENSURE(outs, n * sizeof(ImageOut)); ENSURE(state, ntiles * sizeof(TileState));
+    CK(cudaMemsetAsync(ctx->state.p, 0, ntiles * sizeof(TileState), ctx->stream));
+    const TileDesc* d_tiles = (const TileDesc*)ctx->tiles.p;
+    const ImageDesc* d_imgs = (const ImageDesc*)ctx->imgs.p;
+    const uint32_t* d_seg_tile = (const uint32_t*)ctx->seg_tile.p;
+
+    if (any1 || any2) {
+        const int hstride = any2 ? HIST_STRIDE_M2 : HIST_STRIDE_M1;
+        ENSURE(costs, ntiles * 16); ENSURE(hist, (size_t)ntiles * hstride * 4); ENSURE(seginfo, nseg * sizeof(SegInfo));
+        ENSURE(place, nseg * sizeof(SegPlace)); ENSURE(sym_area, (size_t)nseg * SEG); ENSURE(bits_area, (size_t)nseg * SEG_BITS_BYTES + 64);
+        ENSURE(streams, P.str_total); ENSURE(blocks, P.blk_total);
+        if (P.any_rgba) ENSURE(alpha, P.px_total);
+        CK(cudaMemsetAsync(ctx->costs.p, 0, ntiles * 16, ctx->stream));
+        CK(cudaMemsetAsync(ctx->hist.p, 0, (size_t)ntiles * hstride * 4, ctx->stream));
+        LAUNCH(k_predictor_cost, dim3(ntiles, PP_SPLIT), 256, 0, d_tiles, (const uint8_t*)nullptr, (uint32_t*)ctx->costs.p);
+    }
+    if (any1) {
+        FrontArgs fa{ d_tiles, d_seg_tile, nullptr, (const uint32_t*)ctx->costs.p, nullptr, (SegInfo*)ctx->seginfo.p,
+                      (uint8_t*)ctx->sym_area.p, (uint8_t*)ctx->bits_area.p, (uint8_t*)ctx->alpha.p, (uint32_t*)ctx->hist.p, nullptr };
+        LAUNCH(k_front<1>, nseg, FRONT_THREADS, 0, fa);
+        TileScanArgs ta{ d_tiles, (const SegInfo*)ctx->seginfo.p, (const uint32_t*)ctx->costs.p, nullptr, (SegPlace*)ctx->place.p, nullptr,
+                         (uint32_t*)ctx->hist.p, (TileState*)ctx->state.p, nullptr, ntiles };
+        LAUNCH(k_tile_scan<1>, (ntiles + 3) / 4, 128, 0, ta);
+        CompactArgs ca{ d_tiles, d_seg_tile, (const SegInfo*)ctx->seginfo.p, (const SegPlace*)ctx->place.p, nullptr, nullptr,
+                        (const TileState*)ctx->state.p, (const uint8_t*)ctx->sym_area.p, (const uint8_t*)ctx->bits_area.p,
+                        (uint8_t*)ctx->streams.p, nullptr };
+        LAUNCH(k_compact<1>, nseg, 256, 0, ca);
+        RansV2Args ra{ d_tiles, (TileState*)ctx->state.p, (uint32_t*)ctx->hist.p, (const uint8_t*)ctx->streams.p,
+                       (const uint8_t*)ctx->alpha.p, (uint8_t*)ctx->blocks.p, ntiles, 0, 9 };
+        auto k_small = k_rans_v2<9, 128>; auto k_big = k_rans_v2<256, 32>;
+        LAUNCH(k_small, (9 * ntiles + 127) / 128, 128, 9 * 128 * 16, ra);
+        if (P.any_rgba) {
+            ra.c0 = 9; ra.nc = 1;
+            LAUNCH(k_big, (ntiles + 31) / 32, 32, 256 * 32 * 16, ra);
+        }
+    }
+    if (any2) {
+        if (m2_encode_tiles(ctx, P, ntiles, nseg)) return 1;
+    }
+    LAUNCH(k_image_sizes, (n + 127) / 128, 128, 0, d_imgs, d_tiles, (TileState*)ctx->state.p, (ImageOut*)ctx->outs.p, n);
+    LAUNCH(k_image_offsets, 1, 1, 0, (ImageOut*)ctx->outs.p, n, out_base);
+    {
+        AssembleArgs aa{ d_imgs, d_tiles, (const TileState*)ctx->state.p, (const ImageOut*)ctx->outs.p, (const SegInfo*)ctx->seginfo.p,
+                         (const SegPlace*)ctx->place.p, nullptr, (const uint8_t*)ctx->bits_area.p, (const uint8_t*)ctx->blocks.p, dout };
+        if (any2) { if (m2_assemble(ctx, aa, ntiles)) return 1; }
+        else LAUNCH(k_assemble_m1, ntiles, 256, 0, aa);
+    }
+    if (ensure_pin(ctx, ctx->pin_b, n * sizeof(ImageOut))) return 1;
+    CK(cudaMemcpyAsync(ctx->pin_b.p, ctx->outs.p, n * sizeof(ImageOut), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const ImageOut* ho = (const ImageOut*)ctx->pin_b.p;
+    uint64_t end = out_base;
+    for (uint32_t i = 0; i < n; i++) {
+        out_offsets[i] = ho[i].off; out_sizes[i] = ho[i].size;
+        imgs[i].A = pxsz[i] == 4; imgs[i].mode = ho[i].mode & 0xFF;
+        end = ho[i].off + ((ho[i].size + 15) & ~15ull);
+    }
+    if (end > out_cap) FAIL("output buffer too small: need %llu bytes, have %llu", (unsigned long long)end, (unsigned long long)out_cap);
+    *used = end;
+    return 0;
+}
+
+extern "C" int xpngb_encode(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32_t n, const void* pixels, uint64_t pixels_size,
+                            int pixels_on_device, void* out, uint64_t out_cap, int out_on_device, uint64_t* out_offsets,
+                            uint64_t* out_sizes) {
+    if (!ctx) return 1;
+    ctx->err[0] = 0; ctx->launches = 0; ctx->last_ms = 0.f;
+    if (!imgs || !pixels || !out || !out_offsets || !out_sizes) FAIL("null argument");
+    if (!(level == 1 || level == 2 || level == 7)) FAIL("level must be 1, 2 or 7");          // libxpng.c:729
+    if (n == 0) return 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const xpngb_image& m = imgs[i];
+        if (!m.w || !m.h || m.w > (1u << 24) || m.h > (1u << 24)) FAIL("image %u: bad dimensions", i);   // libxpng.c:729-730
+        if (m.offset & 15) FAIL("image %u: pixel offset must be a multiple of 16", i);
+        if (m.offset + m.w * m.h * (3 + (m.A ? 1 : 0)) > pixels_size) FAIL("image %u: pixels exceed the buffer", i);
+    }
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t bound = xpngb_encode_bound(imgs, n);
+    if (out_on_device && out_cap < bound) FAIL("device output buffer must hold xpngb_encode_bound() = %llu bytes", (unsigned long long)bound);
+    const uint8_t* dpix = (const uint8_t*)pixels;
+    if (!pixels_on_device) {
+        ENSURE(pixels, pixels_size);
+        CK(cudaMemcpyAsync(ctx->pixels.p, pixels, pixels_size, cudaMemcpyHostToDevice, ctx->stream));
+        dpix = (const uint8_t*)ctx->pixels.p;
+    }
+    uint8_t* dout = (uint8_t*)out;
+    if (!out_on_device) { ENSURE(arena, bound); dout = (uint8_t*)ctx->arena.p; }
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    uint64_t used = 0;
+    if (level == 7) {
+        // stored files need no tiles: header + copy (normalisation still applies to RGBA inputs)
+        bool any_rgba = false;
+        for (uint32_t i = 0; i < n; i++) any_rgba |= imgs[i].A != 0;
+        if (!any_rgba) {
+            std::vector<ImageDesc> I(n); std::vector<uint64_t> offs(n);
+            for (uint32_t i = 0; i < n; i++) {
+                I[i] = ImageDesc{}; I[i].px_off = (uint64_t)(dpix + imgs[i].offset); I[i].w = (uint32_t)imgs[i].w; I[i].h = (uint32_t)imgs[i].h;
+                I[i].pxsz = 3; I[i].raw_size = imgs[i].w * imgs[i].h * 3;
+                offs[i] = used; out_offsets[i] = used; out_sizes[i] = 8 + I[i].raw_size; used += (out_sizes[i] + 15) & ~15ull;
+                imgs[i].mode = 7;
+            }
+            ENSURE(imgs, n * sizeof(ImageDesc)); ENSURE(offs, n * 8);
+            if (ensure_pin(ctx, ctx->pin_a, n * (sizeof(ImageDesc) + 8))) return 1;
+            memcpy(ctx->pin_a.p, I.data(), n * sizeof(ImageDesc)); memcpy((uint8_t*)ctx->pin_a.p + n * sizeof(ImageDesc), offs.data(), n * 8);
+            CK(cudaMemcpyAsync(ctx->imgs.p, ctx->pin_a.p, n * sizeof(ImageDesc), cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->offs.p, (uint8_t*)ctx->pin_a.p + n * sizeof(ImageDesc), n * 8, cudaMemcpyHostToDevice, ctx->stream));
+            LAUNCH(k_store7, dim3(296, n), 256, 0, (const ImageDesc*)ctx->imgs.p, (const uint64_t*)ctx->offs.p, dout);
+        } else if (encode_chunk(ctx, 7, imgs, n, dpix, dout, 0, out_on_device ? out_cap : bound, out_offsets, out_sizes, &used)) return 1;
+    } else {
+        uint32_t i0 = 0;
+        while (i0 < n) {
+            uint64_t px = 0; uint32_t i1 = i0;
+            while (i1 < n && (i1 == i0 || px + imgs[i1].w * imgs[i1].h <= ctx->max_chunk_px)) { px += imgs[i1].w * imgs[i1].h; i1++; }
+            if (encode_chunk(ctx, level, imgs + i0, i1 - i0, dpix, dout, used, out_on_device ? out_cap : bound, out_offsets + i0,
+                             out_sizes + i0, &used)) return 1;
+            i0 = i1;
+        }
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (!out_on_device) {
+        if (used > out_cap) {   // sizes are known only now; fail cleanly like a short write would
+            CK(cudaStreamSynchronize(ctx->stream));
+            FAIL("output buffer too small: need %llu bytes, have %llu", (unsigned long long)used, (unsigned long long)out_cap);
+        }
+        CK(cudaMemcpyAsync(out, dout, used, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decode
+// ------------------------------------------------------------------------------------------------
+extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const void* files, uint64_t files_size, int files_on_device,
+                            const uint64_t* file_offsets, const uint64_t* file_sizes, void* pixels, uint64_t pixels_cap,
+                            int pixels_on_device) {
+    if (!ctx) return 1;
+    ctx->err[0] = 0; ctx->launches = 0; ctx->last_ms = 0.f;
+    if (!imgs || !files || !file_offsets || !file_sizes || !pixels) FAIL("null argument");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    for (uint32_t i = 0; i < n; i++) {
+        if (file_sizes[i] < 11 || file_offsets[i] + file_sizes[i] > files_size) FAIL("file %u: bad offset/size", i);
+    }
+    const uint8_t* din = (const uint8_t*)files;
+    if (!files_on_device) {
+        ENSURE(files, files_size);
+        CK(cudaMemcpyAsync(ctx->files.p, files, files_size, cudaMemcpyHostToDevice, ctx->stream));
+        din = (const uint8_t*)ctx->files.p;
+    }
+    // ---- headers (libxpng.c:969-973)
+    std::vector<uint32_t> hdr(2 * n);
+    if (!files_on_device) {
+        for (uint32_t i = 0; i < n; i++) memcpy(&hdr[2 * i], (const uint8_t*)files + file_offsets[i], 8);
+    } else {
+        ENSURE(offs, n * 8); ENSURE(hdr, n * 8);
+        if (ensure_pin(ctx, ctx->pin_a, n * 8)) return 1;
+        memcpy(ctx->pin_a.p, file_offsets, n * 8);
+        CK(cudaMemcpyAsync(ctx->offs.p, ctx->pin_a.p, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(k_gather_headers, (n + 127) / 128, 128, 0, din, (const uint64_t*)ctx->offs.p, n, (uint32_t*)ctx->hdr.p);
+        CK(cudaMemcpyAsync(hdr.data(), ctx->hdr.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    uint8_t* dpx = (uint8_t*)pixels;
+    if (!pixels_on_device) { ENSURE(pixels, pixels_cap); dpx = (uint8_t*)ctx->pixels.p; }
+    Plan P;
+    std::vector<DecImage> DI(n);
+    bool any1 = false, any2 = false;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint64_t w = (hdr[2 * i] & 0xFFFFFFu) + 1, h = (hdr[2 * i + 1] & 0xFFFFFFu) + 1;
+        const uint32_t A = (hdr[2 * i + 1] >> 24) & 1, mode = hdr[2 * i] >> 24, pxsz = 3 + A;
+        if (!(mode == 1 || mode == 2 || mode == 7)) FAIL("file %u: unknown mode %u", i, mode);   // libxpng.c:972
+        if (imgs[i].w && (imgs[i].w != w || imgs[i].h != h)) FAIL("file %u: header %llux%llu does not match the descriptor", i,
+                                                                   (unsigned long long)w, (unsigned long long)h);
+        imgs[i].w = w; imgs[i].h = h; imgs[i].A = A; imgs[i].mode = mode;
+        const uint64_t s = w * h * pxsz;
+        if (imgs[i].offset & 15) FAIL("file %u: pixel offset must be a multiple of 16", i);
+        if (imgs[i].offset + s > pixels_cap) FAIL("file %u: pixels exceed the output buffer", i);
+        uint32_t m = mode;
+        if (mode == 7) { if (file_sizes[i] < 8 + s) FAIL("file %u: truncated stored image", i); }
+        else if (file_sizes[i] == 11 + A && ((hdr[2 * i + 1] >> 24) & 2)) m = mode | 0x100;      // libxpng.c:976
+        any1 |= m == 1; any2 |= m == 2;
+        DecImage& D = DI[i];
+        D.file_off = file_offsets[i]; D.file_size = file_sizes[i]; D.px_off = imgs[i].offset; D.w = (uint32_t)w; D.h = (uint32_t)h;
+        D.pxsz = pxsz; D.mode = m;
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        plan_image(P, (uint64_t)(dpx + imgs[i].offset), DI[i].w, DI[i].h, DI[i].pxsz, DI[i].mode, any2 ? 4 : 1, 0);
+        DI[i].tile0 = P.imgs[i].tile0; DI[i].ntiles = P.imgs[i].ntiles;
+    }
+    const uint32_t ntiles = (uint32_t)P.tiles.size();
+    if (upload_plan(ctx, P)) return 1;
+    ENSURE(dimgs, n * sizeof(DecImage)); ENSURE(dtiles, ntiles * sizeof(DecTile)); ENSURE(errflag, 4);
+    if (ensure_pin(ctx, ctx->pin_b, n * sizeof(DecImage) + 64)) return 1;
+    memcpy(ctx->pin_b.p, DI.data(), n * sizeof(DecImage));
+    CK(cudaMemcpyAsync(ctx->dimgs.p, ctx->pin_b.p, n * sizeof(DecImage), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->errflag.p, 0, 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->dtiles.p, 0, ntiles * sizeof(DecTile), ctx->stream));
+    const TileDesc* d_tiles = (const TileDesc*)ctx->tiles.p;
+    const DecImage* d_imgs = (const DecImage*)ctx->dimgs.p;
+    DecTile* d_dt = (DecTile*)ctx->dtiles.p;
+    int* d_err = (int*)ctx->errflag.p;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (any1 || any2) {
+        ENSURE(streams, P.str_total); ENSURE(nlseq, P.px_total); ENSURE(rows, P.row_total * sizeof(RowInfo));
+        ENSURE(rowbits, P.row_total * 4); ENSURE(rowcnt, P.row_total * 4); ENSURE(edge, P.row_total * 16);
+        if (P.any_rgba) { ENSURE(alpha, P.px_total); ENSURE(plane, P.px_total); }
+        LAUNCH(k_dec_tile_offsets, (n + 127) / 128, 128, 0, d_imgs, din, d_dt, n, d_err);
+    }
+    if (any1) {
+        LAUNCH(k_dec_parse_m1, (ntiles + 127) / 128, 128, 0, d_tiles, d_imgs, din, d_dt, ntiles, d_err);
+        RansDecArgs ra{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, (uint8_t*)ctx->alpha.p, ntiles, 0, 9 };
+        LAUNCH(k_dec_rans_v2_small<128>, (9 * ntiles + 127) / 128, 128, 0, ra);
+        if (P.any_rgba) {
+            LAUNCH(k_dec_rans_v2_big<32>, (ntiles + 31) / 32, 32, 32 * 258 * 2 + 32 * 260, ra);
+            AlphaArgs al{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->alpha.p, (uint8_t*)ctx->plane.p, (uint32_t*)ctx->rowcnt.p };
+            LAUNCH(k_dec_alpha, ntiles, 256, 0, al);
+        }
+        WalkArgs wa{ d_tiles, d_imgs, d_dt, (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->nlseq.p, ntiles, 1 };
+        LAUNCH(k_dec_walk<32>, (ntiles + 31) / 32, 32, 0, wa);
+        RowArgs rw{ d_tiles, d_imgs, d_dt, (const uint8_t*)ctx->nlseq.p, (const uint32_t*)ctx->rowcnt.p, (uint32_t*)ctx->rowbits.p,
+                    (RowInfo*)ctx->rows.p, 1 };
+        LAUNCH(k_dec_rows, ntiles, 256, 0, rw);
+        UnpredArgs ua{ d_tiles, d_imgs, d_dt, din, (const uint8_t*)ctx->nlseq.p, (const uint8_t*)ctx->plane.p, (const RowInfo*)ctx->rows.p,
+                       nullptr, (uint4*)ctx->edge.p };
+        LAUNCH(k_dec_unpredict_m1, ntiles, UNP_THREADS, 0, ua);
+    }
+    if (any2) {
+        if (m2_decode_tiles(ctx, P, d_imgs, d_dt, din, ntiles)) return 1;
+    }
+    LAUNCH(k_dec_copy, ntiles, 256, 0, d_tiles, d_imgs, (const DecTile*)d_dt, din, (uint8_t*)nullptr);
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    int herr = 0;
+    CK(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!pixels_on_device) {
+        uint64_t hi = 0;
+        for (uint32_t i = 0; i < n; i++) { const uint64_t e = imgs[i].offset + imgs[i].w * imgs[i].h * (3 + imgs[i].A); if (e > hi) hi = e; }
+        CK(cudaMemcpyAsync(pixels, dpx, hi, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    if (herr) FAIL("corrupt .xpng data (decoder error %d)", herr);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// YCoCg-R side component
+// ------------------------------------------------------------------------------------------------
+extern "C" int xpngb_ycocg_forward(xpngb_ctx* ctx, const uint8_t* rgb, int16_t* ycc, uint64_t n) {
+    if (!ctx || !rgb || !ycc) return 1;
+    CK(cudaSetDevice(ctx->device));
+    ENSURE(m2a, 3 * n); ENSURE(m2b, 6 * n);
+    CK(cudaMemcpyAsync(ctx->m2a.p, rgb, 3 * n, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(k_ycocg_fwd, 1184, 256, 0, (const uint8_t*)ctx->m2a.p, (int16_t*)ctx->m2b.p, n);
+    CK(cudaMemcpyAsync(ycc, ctx->m2b.p, 6 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int xpngb_ycocg_inverse(xpngb_ctx* ctx, const int16_t* ycc, uint8_t* rgb, uint64_t n) {
+    if (!ctx || !rgb || !ycc) return 1;
+    CK(cudaSetDevice(ctx->device));
+    ENSURE(m2a, 3 * n); ENSURE(m2b, 6 * n);
+    CK(cudaMemcpyAsync(ctx->m2b.p, ycc, 6 * n, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(k_ycocg_inv, 1184, 256, 0, (const int16_t*)ctx->m2b.p, (uint8_t*)ctx->m2a.p, n);
+    CK(cudaMemcpyAsync(rgb, ctx->m2a.p, 3 * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
