@@ -1,0 +1,149 @@
+"""GPU parity tests proper (B200): the CUDA path, called through the C ABI, against the CPU oracle,
+the committed golden manifest (sha256 of files written by the unmodified reference) and, when it
+travelled with the snapshot, the reference binary itself.  Bit-exact everywhere (integer codec)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, all_cases, make_case, manifest, sha
+from oracle import pyoracle as po
+from xpng_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def codec():
+    import xpng_b200
+    cd = xpng_b200.Codec(0)
+    yield cd
+    cd.close()
+
+
+@pytest.mark.parametrize("group,name,entry", all_cases(("synthetic", "special", "crops", "corpus"), big=True),
+                         ids=lambda v: v if isinstance(v, str) else "")
+def test_golden_bytes_and_roundtrip(codec, group, name, entry):
+    px = make_case(group, name, entry)
+    for lv in (1, 2, 7):
+        f = codec.encode(lv, [px])[0]
+        assert len(f) == entry["levels"][str(lv)]["size"], (name, lv)
+        assert sha(f) == entry["levels"][str(lv)]["sha256"], (name, lv)
+        back = codec.decode([f])[0]
+        assert list(back.shape) == entry["decoded_shape"]
+        assert sha(back.tobytes()) == entry["decoded_sha256"], (name, lv)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_shapes_against_oracle(codec, seed):
+    rng = np.random.default_rng(1000 + seed)
+    h, w = int(rng.integers(4, 1200)), int(rng.integers(4, 1400))
+    gen = [synth.rgb, synth.rgba, synth.gray_as_rgb, synth.noise][seed % 4]
+    px = gen(h, w, 700 + seed)
+    for lv in (1, 2, 7):
+        want = po.encode(lv, px)
+        got = codec.encode(lv, [px])[0]
+        assert got == want, (h, w, lv)
+        assert np.array_equal(codec.decode([want])[0], po.normalize(px))
+
+
+def test_batch_mixed_shapes(codec):
+    """Several images of different shapes / alpha in one call: every file equals the single-image oracle file."""
+    imgs = [synth.rgb(300 + 37 * i, 500 + 91 * i, 40 + i) for i in range(5)] + [synth.rgba(400, 333, 50), synth.gray_as_rgb(200, 700, 51),
+            np.full((64, 64, 3), 9, np.uint8), synth.rgb(1, 1, 3)]
+    for lv in (1, 2, 7):
+        got = codec.encode(lv, imgs)
+        assert got == [po.encode(lv, im) for im in imgs]
+        back = codec.decode(got)
+        for b, im in zip(back, imgs):
+            assert np.array_equal(b, po.normalize(im))
+
+
+def test_frame_sequence_config3(codec):
+    """BASELINE config 3 in small: a batch of 1080p 'sintel-like' frames, level 1 and 2."""
+    frames = [synth.sintel_like(1000 + i) for i in range(6)]
+    man = manifest()["synthetic"]
+    for lv in (1, 2):
+        files = codec.encode(lv, frames)
+        assert sha(files[0]) == man["sintel_1080p_s1000"]["levels"][str(lv)]["sha256"]
+        assert sha(files[1]) == man["sintel_1080p_s1001"]["levels"][str(lv)]["sha256"]
+        for f, fr in zip(files, frames):
+            assert f == po.encode(lv, fr)
+        for b, fr in zip(codec.decode(files), frames):
+            assert np.array_equal(b, fr)
+
+
+def test_rgba_tiny_is_rejected(codec):
+    px = synth.rgb(5, 3, 1, channels=4); px[..., 3] = 128
+    with pytest.raises(RuntimeError):
+        codec.encode(1, [px])
+    assert len(codec.encode(7, [px])[0]) == 8 + px.size      # stored is fine
+
+
+def test_corrupt_input_fails_cleanly(codec):
+    f = bytearray(po.encode(1, synth.rgb(300, 300, 5)))
+    f[9] ^= 0xFF; f[10] ^= 0x7F        # first tile's size field
+    with pytest.raises(RuntimeError):
+        codec.decode([bytes(f)])
+    with pytest.raises((RuntimeError, ValueError)):
+        codec.decode([b"\0" * 16])
+
+
+def test_device_resident_buffers(codec):
+    """Device pointers in, device pointers out (what bench.py times as `value`)."""
+    import torch
+    import xpng_b200
+    frames = [synth.rgb(720, 1280, 60 + i) for i in range(3)]
+    descs, total = xpng_b200.Codec.layout([f.shape for f in frames])
+    host = np.zeros(total, np.uint8)
+    for d, f in zip(descs, frames):
+        host[d.offset: d.offset + f.size] = f.reshape(-1)
+    dpx = torch.from_numpy(host).cuda()
+    cap = int(xpng_b200.lib().xpngb_encode_bound(descs, 3))
+    dout = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    offs, sizes = codec.encode_raw(1, descs, 3, dpx.data_ptr(), total, 1, dout.data_ptr(), cap, 1)
+    out = dout.cpu().numpy()
+    files = [out[offs[i]: offs[i] + sizes[i]].tobytes() for i in range(3)]
+    assert files == [po.encode(1, f) for f in frames]
+    dback = torch.zeros(total, dtype=torch.uint8, device="cuda")
+    for d in descs:
+        d.w = d.h = 0   # let the decoder fill them from the headers
+    codec.decode_raw(descs, 3, dout.data_ptr(), cap, 1, offs, sizes, dback.data_ptr(), total, 1)
+    assert np.array_equal(dback.cpu().numpy(), host)
+
+
+def test_file_api_and_cli_against_reference(codec, tmp_path):
+    """xpng_store / xpng_load (xpng.h) and the CLI contract of xpng.c / test.rb: .7 -> .xpng -> .7 + cmp."""
+    import xpng_b200
+    cli = os.path.join(ROOT, "xpng_b200", "bin", "xpng")
+    for px in (synth.rgb(333, 517, 8), synth.rgba(250, 300, 9)):
+        src = str(tmp_path / "src.7"); po.write_7(src, px)
+        for lv in (1, 2, 7):
+            dst, back = str(tmp_path / "res.xpng"), str(tmp_path / "res.7")
+            r = subprocess.run([cli, f"-{lv}", src, dst], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            assert open(dst, "rb").read() == po.encode(lv, px)
+            if lv != 7:
+                assert r.stdout.startswith("encode,") and r.stdout.rstrip().endswith("MPx/s")   # libxpng.c:761
+            r = subprocess.run([cli, "-d", dst, back], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            assert np.array_equal(po.read_7(back), po.normalize(px))
+            # library entry points directly
+            assert xpng_b200.xpng_store(lv, px, dst) is False
+            assert open(dst, "rb").read() == po.encode(lv, px)
+            assert np.array_equal(xpng_b200.xpng_load(dst), po.normalize(px))
+            if po.ref_available():   # the unmodified reference decodes our file, and we decode its file
+                assert np.array_equal(po.ref_decode(open(dst, "rb").read()), po.normalize(px))
+                assert np.array_equal(codec.decode([po.ref_encode(lv, px)])[0], po.normalize(px))
+
+
+def test_ycocg_r_side_kernel(codec):
+    """Tell_Me_Why/YCoCg-R.c: exhaustive 2^24 reversibility and ranges, on the device."""
+    r, g, b = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
+    rgb = np.stack([r, g, b], axis=-1).reshape(-1, 3)
+    ycc = codec.ycocg_forward(rgb)
+    assert ycc[:, 0].min() == 0 and ycc[:, 0].max() == 255
+    assert ycc[:, 1].min() == -255 and ycc[:, 1].max() == 255 and ycc[:, 2].min() == -255 and ycc[:, 2].max() == 255
+    assert np.array_equal(codec.ycocg_inverse(ycc), rgb)

@@ -23,7 +23,8 @@ struct PinBuf { void* p = nullptr; size_t cap = 0; };
 struct xpngb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, pe0 = nullptr, pe1 = nullptr;
+    int profile = 0;   // XPNGB_PROFILE=1: per-kernel CUDA-event timing on stderr (serialises the launches)
     char err[512] = { 0 };
     float last_ms = 0.f;
     uint32_t launches = 0;
@@ -48,11 +49,17 @@ struct xpngb_ctx {
         snprintf(ctx->err, sizeof ctx->err, __VA_ARGS__);        \
         return 1;                                                \
     } while (0)
-#define LAUNCH(kernel, grid, block, smem, ...)                   \
-    do {                                                         \
-        kernel<<<grid, block, smem, ctx->stream>>>(__VA_ARGS__); \
-        ctx->launches++;                                         \
-        CK(cudaGetLastError());                                  \
+#define LAUNCH(kernel, grid, block, smem, ...)                                                      \
+    do {                                                                                            \
+        if (ctx->profile) cudaEventRecord(ctx->pe0, ctx->stream);                                   \
+        kernel<<<grid, block, smem, ctx->stream>>>(__VA_ARGS__);                                    \
+        ctx->launches++;                                                                            \
+        CK(cudaGetLastError());                                                                     \
+        if (ctx->profile) {                                                                         \
+            float ms_ = 0; cudaEventRecord(ctx->pe1, ctx->stream); cudaEventSynchronize(ctx->pe1);  \
+            cudaEventElapsedTime(&ms_, ctx->pe0, ctx->pe1);                                         \
+            fprintf(stderr, "[xpngb] %-28s %9.3f ms\n", #kernel, ms_);                             \
+        }                                                                                           \
     } while (0)
 
 static int ensure(xpngb_ctx* ctx, DevBuf& b, size_t n) {
@@ -167,6 +174,7 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) { delete ctx; return 1; }
+    if (const char* e = getenv("XPNGB_PROFILE")) { ctx->profile = atoi(e); cudaEventCreate(&ctx->pe0); cudaEventCreate(&ctx->pe1); }
     if (const char* e = getenv("XPNGB_CHUNK_MPIX")) { const long v = atol(e); if (v > 0) ctx->max_chunk_px = (uint64_t)v << 20; }
     { auto k_big = k_rans_v2<256, 32>; cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 16); }
     m2_set_attributes();
