@@ -12,7 +12,9 @@
 #include "common.cuh"
 #include "enc_front.cuh"
 #include "enc_back.cuh"
+#include "enc_m2.cuh"
 #include "dec_m1.cuh"
+#include "dec_back.cuh"
 #include "misc.cuh"
 
 using namespace xpb;
@@ -32,7 +34,7 @@ struct xpngb_ctx {
     // device scratch
     DevBuf pixels, norm, files, arena, tiles, imgs, seg_tile, costs, hist, seginfo, place, vplace, vcnt, sym_area,
         bits_area, alpha, streams, blocks, state, outs, flags, skip, dimgs, dtiles, plane, nlseq, rowcnt, rowbits,
-        rows, edge, errflag, hdr, offs, m2a, m2b;
+        rows, edge, errflag, hdr, offs, m2a, m2b, tclass, tabs, ccnt, cbit, resv;
     PinBuf pin_a, pin_b;
 };
 
@@ -156,10 +158,48 @@ static int upload_plan(xpngb_ctx* ctx, const Plan& P) {
 // ------------------------------------------------------------------------------------------------
 // Level 2 host side
 // ------------------------------------------------------------------------------------------------
-static void m2_set_attributes() {}
-static int m2_encode_tiles(xpngb_ctx* ctx, const Plan&, uint32_t, uint32_t) { FAIL("level 2 encode not implemented yet"); }
-static int m2_assemble(xpngb_ctx* ctx, const AssembleArgs&, uint32_t) { FAIL("level 2 encode not implemented yet"); }
-static int m2_decode_tiles(xpngb_ctx* ctx, const Plan&, const DecImage*, DecTile*, const uint8_t*, uint32_t) { FAIL("level 2 decode not implemented yet"); }
+static void m2_set_attributes() {
+    auto k_big = k_rans_v1<256, 32>;
+    cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 16);
+}
+
+// classification, RGB front end (contexts + value streams), grey candidates, backward rANS, size decisions
+static int m2_encode_tiles(xpngb_ctx* ctx, const Plan& P, uint32_t ntiles, uint32_t nseg) {
+    const TileDesc* d_tiles = (const TileDesc*)ctx->tiles.p;
+    const uint32_t* d_seg_tile = (const uint32_t*)ctx->seg_tile.p;
+    ENSURE(tclass, ntiles); ENSURE(skip, ntiles); ENSURE(tabs, (size_t)ntiles * 17 * TAB_WORDS * 4);
+    ENSURE(vplace, nseg * sizeof(SegPlace)); ENSURE(vcnt, (size_t)nseg * 9 * 2);
+    (void)P;
+    LAUNCH(k_m2_classify, ntiles, 256, 0, d_tiles, (const ImageDesc*)ctx->imgs.p, (uint8_t*)ctx->tclass.p);
+    LAUNCH(k_m2_skipmask, (ntiles + 255) / 256, 256, 0, (const uint8_t*)ctx->tclass.p, (uint8_t*)ctx->skip.p, ntiles);
+    FrontArgs fa{ d_tiles, d_seg_tile, nullptr, (const uint32_t*)ctx->costs.p, (const uint8_t*)ctx->skip.p, (SegInfo*)ctx->seginfo.p,
+                  (uint8_t*)ctx->sym_area.p, (uint8_t*)ctx->bits_area.p, nullptr, (uint32_t*)ctx->hist.p, (uint16_t*)ctx->vcnt.p };
+    LAUNCH(k_front<2>, nseg, FRONT_THREADS, 0, fa);
+    TileScanArgs ta{ d_tiles, (const SegInfo*)ctx->seginfo.p, (const uint32_t*)ctx->costs.p, (const uint16_t*)ctx->vcnt.p,
+                     (SegPlace*)ctx->place.p, (SegPlace*)ctx->vplace.p, (uint32_t*)ctx->hist.p, (TileState*)ctx->state.p,
+                     (const uint8_t*)ctx->skip.p, ntiles };
+    LAUNCH(k_tile_scan<2>, (ntiles + 3) / 4, 128, 0, ta);
+    CompactArgs ca{ d_tiles, d_seg_tile, (const SegInfo*)ctx->seginfo.p, (const SegPlace*)ctx->place.p, (const SegPlace*)ctx->vplace.p,
+                    (const uint16_t*)ctx->vcnt.p, (const TileState*)ctx->state.p, (const uint8_t*)ctx->sym_area.p,
+                    (const uint8_t*)ctx->bits_area.p, (uint8_t*)ctx->streams.p, (const uint8_t*)ctx->skip.p };
+    LAUNCH(k_compact<2>, nseg, 256, 0, ca);
+    LAUNCH(k_m2_grey_front, nseg, 256, 0, d_tiles, d_seg_tile, (const uint8_t*)ctx->tclass.p, (uint8_t*)ctx->streams.p, (uint32_t*)ctx->hist.p);
+    RansV1Args ra{ d_tiles, (TileState*)ctx->state.p, (const uint32_t*)ctx->hist.p, (const uint8_t*)ctx->tclass.p,
+                   (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->blocks.p, (uint32_t*)ctx->tabs.p, ntiles, 0, 17, 0, 0 };
+    auto k_small = k_rans_v1<16, 128>; auto k_big = k_rans_v1<256, 32>;
+    LAUNCH(k_small, (17 * ntiles + 127) / 128, 128, 16 * 128 * 16, ra);
+    ra.c0 = 9; ra.nc = 8; ra.nmin = 16;
+    LAUNCH(k_big, (8 * ntiles + 31) / 32, 32, 256 * 32 * 16, ra);
+    ra.c0 = 0; ra.nc = 4; ra.nmin = 0; ra.grey = 1;
+    LAUNCH(k_big, (4 * ntiles + 31) / 32, 32, 256 * 32 * 16, ra);
+    LAUNCH(k_m2_finish, (ntiles + 127) / 128, 128, 0, d_tiles, (const uint8_t*)ctx->tclass.p, (TileState*)ctx->state.p, ntiles);
+    return 0;
+}
+static int m2_assemble(xpngb_ctx* ctx, const AssembleArgs& aa, uint32_t ntiles) {
+    AssembleM2Args ma{ aa, (const uint8_t*)ctx->tclass.p, (const uint32_t*)ctx->tabs.p, (const uint8_t*)ctx->streams.p };
+    LAUNCH(k_assemble_m2, ntiles, 256, 0, ma);
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Context
@@ -190,7 +230,7 @@ extern "C" void xpngb_destroy(xpngb_ctx* ctx) {
                       &ctx->hist, &ctx->seginfo, &ctx->place, &ctx->vplace, &ctx->vcnt, &ctx->sym_area, &ctx->bits_area, &ctx->alpha,
                       &ctx->streams, &ctx->blocks, &ctx->state, &ctx->outs, &ctx->flags, &ctx->skip, &ctx->dimgs, &ctx->dtiles,
                       &ctx->plane, &ctx->nlseq, &ctx->rowcnt, &ctx->rowbits, &ctx->rows, &ctx->edge, &ctx->errflag, &ctx->hdr,
-                      &ctx->offs, &ctx->m2a, &ctx->m2b };
+                      &ctx->offs, &ctx->m2a, &ctx->m2b, &ctx->tclass, &ctx->tabs, &ctx->ccnt, &ctx->cbit, &ctx->resv };
     for (DevBuf* b : all) if (b->p) cudaFree(b->p);
     if (ctx->pin_a.p) cudaFreeHost(ctx->pin_a.p);
     if (ctx->pin_b.p) cudaFreeHost(ctx->pin_b.p);
@@ -499,9 +539,12 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
     DecTile* d_dt = (DecTile*)ctx->dtiles.p;
     int* d_err = (int*)ctx->errflag.p;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    const uint32_t nseg = (uint32_t)P.seg_tile.size();
+    const uint32_t* d_seg_tile = (const uint32_t*)ctx->seg_tile.p;
     if (any1 || any2) {
         ENSURE(streams, P.str_total); ENSURE(nlseq, P.px_total); ENSURE(rows, P.row_total * sizeof(RowInfo));
-        ENSURE(rowbits, P.row_total * 4); ENSURE(rowcnt, P.row_total * 4); ENSURE(edge, P.row_total * 16);
+        ENSURE(rowcnt, P.row_total * 4); ENSURE(edge, P.row_total * 16);
+        ENSURE(ccnt, (size_t)nseg * 9 * 4); ENSURE(cbit, (size_t)nseg * 4); ENSURE(resv, P.px_total * 4);
         if (P.any_rgba) { ENSURE(alpha, P.px_total); ENSURE(plane, P.px_total); }
         LAUNCH(k_dec_tile_offsets, (n + 127) / 128, 128, 0, d_imgs, din, d_dt, n, d_err);
     }
@@ -513,18 +556,37 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
             LAUNCH(k_dec_rans_v2_big<32>, (ntiles + 31) / 32, 32, 32 * 258 * 2 + 32 * 260, ra);
             AlphaArgs al{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->alpha.p, (uint8_t*)ctx->plane.p, (uint32_t*)ctx->rowcnt.p };
             LAUNCH(k_dec_alpha, ntiles, 256, 0, al);
+            LAUNCH(k_dec_rows_rgba, ntiles, 32, 0, d_tiles, d_imgs, (const DecTile*)d_dt, (const uint32_t*)ctx->rowcnt.p, (RowInfo*)ctx->rows.p);
         }
-        WalkArgs wa{ d_tiles, d_imgs, d_dt, (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->nlseq.p, ntiles, 1 };
-        LAUNCH(k_dec_walk<32>, (ntiles + 31) / 32, 32, 0, wa);
-        RowArgs rw{ d_tiles, d_imgs, d_dt, (const uint8_t*)ctx->nlseq.p, (const uint32_t*)ctx->rowcnt.p, (uint32_t*)ctx->rowbits.p,
-                    (RowInfo*)ctx->rows.p, 1 };
-        LAUNCH(k_dec_rows, ntiles, 256, 0, rw);
-        UnpredArgs ua{ d_tiles, d_imgs, d_dt, din, (const uint8_t*)ctx->nlseq.p, (const uint8_t*)ctx->plane.p, (const RowInfo*)ctx->rows.p,
-                       nullptr, (uint4*)ctx->edge.p };
-        LAUNCH(k_dec_unpredict_m1, ntiles, UNP_THREADS, 0, ua);
     }
     if (any2) {
-        if (m2_decode_tiles(ctx, P, d_imgs, d_dt, din, ntiles)) return 1;
+        LAUNCH(k_dec_parse_m2, (ntiles + 127) / 128, 128, 0, d_tiles, d_imgs, din, d_dt, ntiles, d_err);
+        RansV1DecArgs rv{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 9, 0, 16 };
+        auto k8 = k_dec_rans_v1_small<8, 128>; auto k15 = k_dec_rans_v1_small<15, 128>; auto kbig = k_dec_rans_v1_big<32>;
+        LAUNCH(k8, (9 * ntiles + 127) / 128, 128, 0, rv);                     // contexts (9 symbols); grey tiles: nothing (N = 256)
+        rv.c0 = 9; rv.nc = 8;
+        LAUNCH(k15, (8 * ntiles + 127) / 128, 128, 0, rv);                    // value alphabets of 8 / 16 symbols
+        rv.nmin = 16; rv.nmax = 256;
+        LAUNCH(kbig, (8 * ntiles + 31) / 32, 32, 32 * 258 * 2 + 32 * 260, rv); // value alphabets of 32..256 symbols
+        rv.c0 = 0; rv.nc = 1;
+        LAUNCH(kbig, (ntiles + 31) / 32, 32, 32 * 258 * 2 + 32 * 260, rv);     // grey planes
+    }
+    if (any1 || any2) {
+        for (uint32_t mode = 1; mode <= 2; mode++) {
+            if (!(mode == 1 ? any1 : any2)) continue;
+            WalkArgs wa{ d_tiles, d_imgs, d_dt, (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->nlseq.p, ntiles, mode };
+            LAUNCH(k_dec_walk<32>, (ntiles + 31) / 32, 32, 0, wa);
+        }
+        ChunkArgs ch{ d_tiles, d_seg_tile, d_imgs, d_dt, (const uint8_t*)ctx->nlseq.p, (const uint8_t*)ctx->streams.p, din,
+                      (uint32_t*)ctx->ccnt.p, (uint32_t*)ctx->cbit.p, (uint32_t*)ctx->resv.p, ntiles, d_err };
+        LAUNCH(k_dec_chunk_hist, nseg, 256, 0, ch);
+        LAUNCH(k_dec_chunk_scan, (ntiles + 3) / 4, 128, 0, ch);
+        if (any1) LAUNCH(k_dec_residuals<1>, nseg, 256, 0, ch);
+        if (any2) { LAUNCH(k_dec_residuals<2>, nseg, 256, 0, ch); LAUNCH(k_dec_residuals_grey, nseg, 256, 0, ch); }
+        UnpredArgs ua{ d_tiles, d_imgs, d_dt, din, (const uint32_t*)ctx->resv.p, (const uint8_t*)ctx->plane.p, (const RowInfo*)ctx->rows.p,
+                       (uint4*)ctx->edge.p };
+        LAUNCH(k_dec_unpredict, ntiles, UNP_THREADS, 0, ua);
+        if (any2) LAUNCH(k_dec_grey_raw, ntiles, 256, 0, d_tiles, d_imgs, (const DecTile*)d_dt, din);
     }
     LAUNCH(k_dec_copy, ntiles, 256, 0, d_tiles, d_imgs, (const DecTile*)d_dt, din, (uint8_t*)nullptr);
     CK(cudaEventRecord(ctx->ev1, ctx->stream));

@@ -72,12 +72,19 @@ struct TileState {
     uint32_t kbits_lo, kbits_hi; // total bits of the side/residual bit stream (incl. first pixel)
     uint32_t len[MAX_STREAMS];   // symbols per stream
     uint32_t soff[MAX_STREAMS];  // byte offset of stream inside the tile's stream slice (16-aligned)
-    uint32_t boff[MAX_STREAMS];  // byte offset of the stream's block scratch inside the tile's block slice
+    uint32_t breg[MAX_STREAMS];  // byte offset of the stream's block scratch region inside the tile's block slice
+    uint32_t boff[MAX_STREAMS];  // byte offset of the finished block (== breg for v2 blocks, end-aligned for v1)
     uint32_t bsize[MAX_STREAMS]; // final block size in bytes
+    uint32_t pbits[MAX_STREAMS]; // level 2: bits this block adds to the tile's shared side stream (table or raw symbols)
+    uint32_t pbo[MAX_STREAMS];   // level 2: bit offset of that piece inside the side stream
+    uint32_t btype[MAX_STREAMS]; // level 2: block type 0..4
     uint32_t size;               // final tile blob size
     uint32_t grey_pick;          // chosen grey predictor (mode 2)
     uint64_t out_off;            // byte offset of the blob in the output arena
 };
+
+// Tile classes of level 2 (libxpng.c:655: single colour, then grey, then RGB)
+enum TileClass { TC_RGB = 0, TC_SINGLE = 1, TC_GREY = 2, TC_NONE = 3 };
 
 // ---------------------------------------------------------------- scalar helpers
 

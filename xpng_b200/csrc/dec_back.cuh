@@ -1,0 +1,512 @@
+// dec_back.cuh — decode back end shared by levels 1 and 2, plus the level-2 front (tile parse, v1
+// rANS decode, libxpng.c:262-301, :868-961).
+//   nl sequence  ->  per-chunk counts  ->  per-tile scan (bit / value offsets)  ->  residual plane
+//   (one packed zig-zag triple per coded pixel)  ->  wavefront un-predict.
+// Everything except the per-tile chunk scan and the wavefront itself is data-parallel.
+#pragma once
+#include "common.cuh"
+#include "enc_front.cuh"   // Cnt9 helpers
+#include "dec_m1.cuh"
+
+namespace xpb {
+
+// Level-2 alphabets (libxpng.c:951): contexts 9, then nl = 1..8 -> 8,64,8,16,32,64,128,256.
+__device__ __constant__ const uint16_t DEC_M2_NSYM[17] = { 9, 9, 9, 9, 9, 9, 9, 9, 9, 8, 64, 8, 16, 32, 64, 128, 256 };
+
+// ------------------------------------------------------------------------------------------------
+// Level-2 tile parse: tile kind, the 17 (or 1) v1 block headers and where each block's frequency
+// table / raw symbols start in the tile's shared side bit stream (type-4 tables are variable
+// length, so the offsets form a short serial chain).  One thread per tile.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_dec_parse_m2(const TileDesc* tiles, const DecImage* imgs, const uint8_t* in, DecTile* dt, uint32_t ntiles, int* err) {
+    const uint32_t tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= ntiles) return;
+    const TileDesc t = tiles[tile];
+    if (imgs[t.img].mode != 2) return;
+    DecTile* d = dt + tile;
+    if (d->m == 0xFE) return;
+    const uint8_t* blob = in + d->blob_off;
+    bool bad = false;
+    if (d->m == 0) bad = d->size != t.npx * 3 + 4;
+    else if (d->m == 0xFF) bad = d->size != 8;
+    else if ((d->m >> 4) == 2 && (d->m & 8)) bad = d->size != t.npx + 4;
+    else if ((d->m >> 4) == 2 || (d->m >> 4) == 1) {
+        const bool grey = (d->m >> 4) == 2;
+        const int nblk = grey ? 1 : 17, pb = grey ? 15 : 14;
+        bad = d->size < 12;
+        uint32_t bsz = bad ? 4 : ld32u(blob + 4);
+        if (bsz < 4 || (uint64_t)4 + bsz > d->size) bad = true;
+        const uint8_t* kend = blob + 4 + bsz;
+        uint32_t off = 4 + bsz, bit = grey ? 8 : 24, soff = 0, nsym = 0;
+        for (int c = 0; c < nblk && !bad; c++) {
+            if (off + 4 > d->size) { bad = true; break; }
+            const uint32_t N = grey ? 256u : (uint32_t)DEC_M2_NSYM[c], nbit = bitlen32(N - 1);
+            const uint32_t w0 = ld32u(blob + off), type = w0 >> 24, bsize = w0 & 0xFFFFFFu;
+            uint32_t n = 0;
+            if (type > 4 || bsize < 4 || off + bsize > d->size || (type && bsize < 8) || (type >= 3 && bsize < 24)) { bad = true; break; }
+            if (type) { n = ld32u(blob + off + 4); if (type == 1) n &= 0xFFFFFFu; }
+            if (n > 3 * t.npx) { bad = true; break; }
+            d->blk[c] = DecBlock{ off, n, type, soff };
+            d->bitpos[c] = bit;
+            if (type == 2) bit += nbit * n;
+            else if (type == 3) bit += N * (uint32_t)pb;
+            else if (type == 4) {
+                BitR r{ blob + 8, kend, bit };
+                for (uint32_t k = 0; k < N; k++) if (r.get(1)) r.pos += (uint32_t)pb;
+                bit = r.pos;
+            }
+            soff += align16u_dec(n);
+            if (c < 9) nsym += n;
+            off += bsize;
+        }
+        if (!bad && nsym != t.npx - 1 && !grey) bad = true;
+        if (!bad && grey && d->blk[0].n != t.npx - 1) bad = true;
+        if (!bad && (uint64_t)bit > 8ull * (bsz - 4)) bad = true;
+        d->bsz = bsz; d->nsym = grey ? t.npx - 1 : nsym;
+    } else bad = true;
+    if (bad) { dec_fail(err, DEC_BAD_BLOCK); d->m = 0xFE; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// v1 block decoder (forward, libxpng.c:262-301): one lane per block.  The frequency table (or the
+// raw symbols of a type-2 block) is read from the tile's shared side stream at bitpos[c].
+// ------------------------------------------------------------------------------------------------
+struct RansV1DecArgs {
+    const TileDesc* tiles;
+    const DecImage* imgs;
+    const DecTile* dt;
+    const uint8_t* in;
+    uint8_t* streams;
+    uint32_t ntiles;
+    uint32_t c0, nc;
+    uint32_t nmin, nmax;   // alphabet sizes handled by this launch: nmin < N <= nmax
+};
+
+#define XPB_RENORM_FWD(x)                                                              \
+    if ((x) < (1ull << 31)) { (x) = ((x) << 32) | wa; wa = wb; if (rp < rend) rp += 4;  \
+        wb = (rp + 8 <= rend) ? ld32u(rp + 4) : 0u; }
+
+// Returns false when the lane has nothing to do; otherwise fills the per-block geometry.
+struct V1Block { const uint8_t* blob; const uint8_t* blk; uint8_t* out; uint32_t n, type, N, bitpos, bsz, bsize; int pb; };
+
+__device__ __forceinline__ bool v1_block_setup(const RansV1DecArgs& A, uint32_t id, V1Block& B) {
+    if (id >= A.nc * A.ntiles) return false;
+    const uint32_t c = A.c0 + id / A.ntiles, tile = id % A.ntiles;
+    const TileDesc t = A.tiles[tile];
+    if (A.imgs[t.img].mode != 2) return false;
+    const DecTile* d = A.dt + tile;
+    const uint32_t kind = d->m >> 4;
+    if (d->m == 0xFE || d->m == 0xFF || d->m == 0 || (kind == 2 && (d->m & 8))) return false;
+    const bool grey = kind == 2;
+    if (grey && c != 0) return false;
+    B.N = grey ? 256u : (uint32_t)DEC_M2_NSYM[c]; B.pb = grey ? 15 : 14;
+    if (B.N <= A.nmin || B.N > A.nmax) return false;
+    const DecBlock b = d->blk[c];
+    B.blob = A.in + d->blob_off; B.blk = B.blob + b.off; B.out = A.streams + t.str_off + b.soff;
+    B.n = b.n; B.type = b.type; B.bitpos = d->bitpos[c]; B.bsz = d->bsz; B.bsize = ld32u(B.blk) & 0xFFFFFFu;
+    if (B.type == 0 || B.n == 0) return false;
+    if (B.type == 1) {
+        const uint32_t v4 = (ld32u(B.blk + 4) >> 24) * 0x01010101u;
+        for (uint32_t k = 0; k < (B.n + 3) / 4; k++) reinterpret_cast<uint32_t*>(B.out)[k] = v4;
+        return false;
+    }
+    if (B.type == 2) {
+        BitR r{ B.blob + 8, B.blob + 4 + B.bsz, B.bitpos };
+        const uint32_t nbit = bitlen32(B.N - 1);
+        for (uint32_t k = 0; k < B.n; k++) B.out[k] = (uint8_t)r.get(nbit);
+        return false;
+    }
+    return true;
+}
+
+template <int NTH, int LANES>
+__global__ void __launch_bounds__(LANES) k_dec_rans_v1_small(RansV1DecArgs A) {
+    __shared__ uint32_t fs[(NTH + 1) * LANES];   // [sym][lane]: start | freq << 16
+    V1Block B;
+    if (!v1_block_setup(A, blockIdx.x * LANES + threadIdx.x, B)) return;
+    const int pb = B.pb;
+    uint32_t th[NTH];
+    {
+        BitR r{ B.blob + 8, B.blob + 4 + B.bsz, B.bitpos };
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i <= NTH; i++) {
+            uint32_t f = 0;
+            if ((uint32_t)i < B.N) f = B.type == 3 ? r.get((uint32_t)pb) : (r.get(1) ? r.get((uint32_t)pb) : 0u);
+            fs[i * LANES + threadIdx.x] = (acc & 0xFFFFu) | (f << 16);
+            acc += f;
+            if (i < NTH) th[i] = (uint32_t)(i + 1) < B.N ? acc : 0xFFFFFFFFu;
+        }
+    }
+    const uint32_t mask = (1u << pb) - 1u;
+    const uint8_t* rend = B.blk + B.bsize; const uint8_t* rp = B.blk + 24;
+    uint64_t x0 = ld64u(B.blk + 8), x1 = ld64u(B.blk + 16);
+    uint32_t wa = (rp + 4 <= rend) ? ld32u(rp) : 0u, wb = (rp + 8 <= rend) ? ld32u(rp + 4) : 0u;
+    auto sym_of = [&](uint64_t x) -> uint32_t {
+        const uint32_t slot = (uint32_t)x & mask; uint32_t s = 0;
+#pragma unroll
+        for (int i = 0; i < NTH; i++) s += slot >= th[i];
+        return s;
+    };
+    auto step = [&](uint64_t& x) -> uint32_t {
+        const uint32_t s = sym_of(x), slot = (uint32_t)x & mask, e = fs[s * LANES + threadIdx.x];
+        x = (uint64_t)(e >> 16) * (x >> pb) + slot - (e & 0xFFFFu);
+        XPB_RENORM_FWD(x)
+        return s;
+    };
+    const uint32_t n = B.n; uint32_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const uint32_t s0 = step(x0), s1 = step(x1), s2 = step(x0), s3 = step(x1);
+        *reinterpret_cast<uint32_t*>(B.out + i) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+    }
+    for (; i < n; i++) B.out[i] = (uint8_t)((i & 1) ? step(x1) : step(x0));
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(LANES) k_dec_rans_v1_big(RansV1DecArgs A) {
+    extern __shared__ __align__(16) uint8_t smem_big[];
+    uint16_t* cumS = reinterpret_cast<uint16_t*>(smem_big) + threadIdx.x * 258;
+    uint8_t* coarse = smem_big + LANES * 258 * 2 + threadIdx.x * 260;
+    V1Block B;
+    if (!v1_block_setup(A, blockIdx.x * LANES + threadIdx.x, B)) return;
+    const int pb = B.pb;
+    {
+        BitR r{ B.blob + 8, B.blob + 4 + B.bsz, B.bitpos };
+        uint32_t acc = 0;
+        for (uint32_t i = 0; i < 256; i++) {
+            cumS[i] = (uint16_t)acc;
+            uint32_t f = 0;
+            if (i < B.N) f = B.type == 3 ? r.get((uint32_t)pb) : (r.get(1) ? r.get((uint32_t)pb) : 0u);
+            acc += f; if (acc > (1u << pb)) acc = 1u << pb;
+        }
+        cumS[256] = (uint16_t)acc;
+        uint32_t s = 0;
+        for (uint32_t k = 0; k < 256; k++) {
+            const uint32_t slot = k << (pb - 8);
+            while (s < 255 && (uint32_t)cumS[s + 1] <= slot) s++;
+            coarse[k] = (uint8_t)s;
+        }
+    }
+    const uint32_t mask = (1u << pb) - 1u;
+    const uint8_t* rend = B.blk + B.bsize; const uint8_t* rp = B.blk + 24;
+    uint64_t x0 = ld64u(B.blk + 8), x1 = ld64u(B.blk + 16);
+    uint32_t wa = (rp + 4 <= rend) ? ld32u(rp) : 0u, wb = (rp + 8 <= rend) ? ld32u(rp + 4) : 0u;
+    auto step = [&](uint64_t& x) -> uint32_t {
+        const uint32_t slot = (uint32_t)x & mask;
+        uint32_t s = coarse[slot >> (pb - 8)];
+        while (s < 255 && (uint32_t)cumS[s + 1] <= slot) s++;
+        const uint32_t start = cumS[s], f = (uint32_t)cumS[s + 1] - start;
+        x = (uint64_t)f * (x >> pb) + slot - start;
+        XPB_RENORM_FWD(x)
+        return s;
+    };
+    const uint32_t n = B.n; uint32_t i = 0;
+    for (; i + 4 <= n; i += 4) {
+        const uint32_t s0 = step(x0), s1 = step(x1), s2 = step(x0), s3 = step(x1);
+        *reinterpret_cast<uint32_t*>(B.out + i) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+    }
+    for (; i < n; i++) B.out[i] = (uint8_t)((i & 1) ? step(x1) : step(x0));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Chunk counts: how many coded pixels of each nl a 4096-entry chunk of the nl sequence holds.
+// ------------------------------------------------------------------------------------------------
+struct ChunkArgs {
+    const TileDesc* tiles;
+    const uint32_t* seg_tile;
+    const DecImage* imgs;
+    const DecTile* dt;
+    const uint8_t* nlseq;
+    const uint8_t* streams;
+    const uint8_t* in;
+    uint32_t* ccnt;      // [nseg][9] counts, then (after the scan) exclusive prefixes per nl
+    uint32_t* cbit;      // [nseg] bit offset of the chunk's first residual (level 1)
+    uint32_t* resv;      // residual plane per tile at px_off: u0 | u1 << 8 | u2 << 16 per coded pixel
+    uint32_t ntiles;
+    int* err;
+};
+
+__device__ __forceinline__ bool coded_tile(const DecTile* d) { return d->m != 0 && d->m < 0x20; }   // RGB entropy-coded tile
+
+__global__ void __launch_bounds__(256) k_dec_chunk_hist(ChunkArgs A) {
+    __shared__ Cnt9 wc[8];
+    const uint32_t gseg = blockIdx.x, tile = A.seg_tile[gseg], tid = threadIdx.x;
+    const TileDesc t = A.tiles[tile];
+    const DecTile* d = A.dt + tile;
+    if (A.imgs[t.img].mode == 7 || (A.imgs[t.img].mode & 0x100) || !coded_tile(d)) return;
+    const uint32_t c0 = (gseg - t.seg0) * SEG;
+    if (c0 >= d->nsym) return;
+    const uint32_t c1 = min(c0 + (uint32_t)SEG, d->nsym);
+    const uint8_t* seq = A.nlseq + t.px_off;
+    Cnt9 cc{ 0, 0, 0 };
+    const uint32_t e0 = c0 + tid * 16;
+    if (e0 < c1) {
+        const uint4 q = *reinterpret_cast<const uint4*>(seq + e0);
+        const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+        for (int e = 0; e < 16; e++) if (e0 + e < c1) cnt9_inc(cc, (w[e >> 2] >> (8 * (e & 3))) & 0xFu);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        cc.a += __shfl_xor_sync(0xffffffffu, cc.a, o); cc.b += __shfl_xor_sync(0xffffffffu, cc.b, o); cc.c += __shfl_xor_sync(0xffffffffu, cc.c, o);
+    }
+    if ((tid & 31) == 0) wc[tid >> 5] = cc;
+    __syncthreads();
+    if (tid < 9) {
+        uint32_t s = 0;
+        for (int k = 0; k < 8; k++) s += cnt9_get(wc[k], tid);
+        A.ccnt[(uint64_t)gseg * 9 + tid] = s;
+    }
+}
+
+// Per-tile exclusive scan of the chunk counts (warp per tile, lane c = nl value).  Also checks the
+// totals against what the bit stream / value streams actually hold.
+__global__ void __launch_bounds__(128) k_dec_chunk_scan(ChunkArgs A) {
+    const uint32_t tile = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (tile >= A.ntiles) return;
+    const TileDesc t = A.tiles[tile];
+    const DecTile* d = A.dt + tile;
+    const uint32_t mode = A.imgs[t.img].mode;
+    if (mode == 7 || (mode & 0x100) || !coded_tile(d)) return;
+    const uint32_t nchunk = (d->nsym + SEG - 1) / SEG;
+    uint32_t run = 0, bit = (mode == 1 ? t.pxsz : 3u) * 8u;
+    for (uint32_t j = 0; j < nchunk; j++) {
+        const uint32_t v = lane < 9 ? A.ccnt[(uint64_t)(t.seg0 + j) * 9 + lane] : 0;
+        if (lane < 9) A.ccnt[(uint64_t)(t.seg0 + j) * 9 + lane] = run;
+        run += v;
+        uint32_t b = 3 * lane * v;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+        if (lane == 0) A.cbit[t.seg0 + j] = bit;
+        bit += b;
+    }
+    bool bad = false;
+    if (mode == 1) bad = (uint64_t)bit > 8ull * (d->bsz - 4);
+    else if (lane >= 1 && lane < 9) bad = run * (lane < 3 ? 1u : 3u) != d->blk[8 + lane].n;
+    if (__any_sync(0xffffffffu, bad) && lane == 0) dec_fail(A.err, DEC_BAD_COUNTS);
+}
+
+// Residual plane: level 1 reads 3*nl bits per coded pixel at its bit offset; level 2 reads 1 or 3
+// bytes from value stream nl at its rank.  CTA per chunk, 16 consecutive entries per thread.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_dec_residuals(ChunkArgs A) {
+    __shared__ uint32_t wsum[8];
+    __shared__ Cnt9 wc[8];
+    const uint32_t gseg = blockIdx.x, tile = A.seg_tile[gseg], tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const TileDesc t = A.tiles[tile];
+    const DecTile* d = A.dt + tile;
+    if (A.imgs[t.img].mode != MODE || !coded_tile(d)) return;
+    const uint32_t c0 = (gseg - t.seg0) * SEG;
+    if (c0 >= d->nsym) return;
+    const uint32_t c1 = min(c0 + (uint32_t)SEG, d->nsym);
+    const uint8_t* seq = A.nlseq + t.px_off;
+    uint32_t* res = A.resv + t.px_off;
+    const uint8_t* blob = A.in + d->blob_off;
+    const uint32_t e0 = c0 + tid * 16;
+    uint32_t w[4] = { 0, 0, 0, 0 };
+    if (e0 < c1) { const uint4 q = *reinterpret_cast<const uint4*>(seq + e0); w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w; }
+    if (MODE == 1) {
+        uint32_t mine = 0;
+#pragma unroll
+        for (int e = 0; e < 16; e++) if (e0 + e < c1) mine += 3 * ((w[e >> 2] >> (8 * (e & 3))) & 0xFu);
+        uint32_t inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+        if (lane == 31) wsum[wid] = inc;
+        __syncthreads();
+        uint32_t bit = A.cbit[gseg] + inc - mine;
+        for (uint32_t k = 0; k < wid; k++) bit += wsum[k];
+        const uint8_t* kb = blob + 8; const uint8_t* kend = blob + 4 + d->bsz;
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            if (e0 + e >= c1) break;
+            const uint32_t nl = (w[e >> 2] >> (8 * (e & 3))) & 0xFu;
+            uint32_t v = 0;
+            if (nl) {
+                const uint8_t* p = kb + 4ull * (bit >> 5);
+                const uint32_t w0 = (p + 4 <= kend) ? ld32u(p) : 0u, sh = bit & 31u;
+                const uint32_t w1 = (sh + 3 * nl > 32 && p + 8 <= kend) ? ld32u(p + 4) : 0u;
+                const uint32_t f = (sh ? ((w0 << sh) | (w1 >> (32u - sh))) : w0) >> (32u - 3 * nl), mk = (1u << nl) - 1u;
+                v = (f >> (2 * nl)) | (((f >> nl) & mk) << 8) | ((f & mk) << 16);
+                bit += 3 * nl;
+            }
+            res[e0 + e] = v;
+        }
+    } else {
+        Cnt9 cc{ 0, 0, 0 };
+#pragma unroll
+        for (int e = 0; e < 16; e++) if (e0 + e < c1) cnt9_inc(cc, (w[e >> 2] >> (8 * (e & 3))) & 0xFu);
+        Cnt9 tot;
+        Cnt9 pos = block_scan_cnt9(cc, wc, tot);
+        uint32_t base[9], pp[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) { base[k] = A.ccnt[(uint64_t)gseg * 9 + k] + cnt9_get(pos, k); pp[k] = d->blk[k < 1 ? 0 : 8 + k].soff; }
+        const uint8_t* sbase = A.streams + t.str_off;
+#pragma unroll
+        for (int e = 0; e < 16; e++) {
+            if (e0 + e >= c1) break;
+            const uint32_t nl = (w[e >> 2] >> (8 * (e & 3))) & 0xFu;
+            uint32_t v = 0;
+            if (nl) {
+                uint32_t rank = 0, so = 0;
+#pragma unroll
+                for (int k = 1; k < 9; k++) if (nl == (uint32_t)k) { rank = base[k]; base[k]++; so = pp[k]; }
+                if (nl == 1) { const uint32_t b = sbase[so + rank]; v = (b >> 2) | (((b >> 1) & 1u) << 8) | ((b & 1u) << 16); }
+                else if (nl == 2) { const uint32_t b = sbase[so + rank]; v = (b >> 4) | (((b >> 2) & 3u) << 8) | ((b & 3u) << 16); }
+                else { const uint8_t* q = sbase + so + 3ull * rank; v = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16); }
+            }
+            res[e0 + e] = v;
+        }
+    }
+}
+
+// Grey tiles: the single decoded plane becomes (u,u,u) residual triples.
+__global__ void __launch_bounds__(256) k_dec_residuals_grey(ChunkArgs A) {
+    const uint32_t gseg = blockIdx.x, tile = A.seg_tile[gseg];
+    const TileDesc t = A.tiles[tile];
+    const DecTile* d = A.dt + tile;
+    if (A.imgs[t.img].mode != 2 || (d->m >> 4) != 2 || (d->m & 8) || d->m == 0xFE || d->m == 0xFF) return;
+    const uint32_t c0 = (gseg - t.seg0) * SEG, c1 = min(c0 + (uint32_t)SEG, t.npx - 1);
+    const uint8_t* s = A.streams + t.str_off + d->blk[0].soff;
+    uint32_t* res = A.resv + t.px_off;
+    for (uint32_t k = c0 + threadIdx.x; k < c1; k += 256) res[k] = (uint32_t)s[k] * 0x010101u;
+}
+
+// Row index table for RGBA tiles: rows[y].idx = coded pixels before row y (from k_dec_alpha's counts).
+__global__ void __launch_bounds__(32) k_dec_rows_rgba(const TileDesc* tiles, const DecImage* imgs, const DecTile* dt, const uint32_t* rowcnt,
+                                                      RowInfo* rows) {
+    const uint32_t tile = blockIdx.x, lane = threadIdx.x;
+    const TileDesc t = tiles[tile];
+    if (imgs[t.img].mode != 1 || t.pxsz != 4) return;
+    const DecTile* d = dt + tile;
+    if (!coded_tile(d)) return;
+    uint32_t run = 0;
+    for (uint32_t y0 = 0; y0 < t.h; y0 += 32) {
+        const uint32_t y = y0 + lane, v = y < t.h ? rowcnt[t.row_off + y] : 0;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
+        if (y < t.h) rows[t.row_off + y].idx = run + inc - v;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Wavefront un-predict (libxpng.c:811-814, :866-897, :911-914).  Thread x owns column x of a strip;
+// at step s it reconstructs pixel (x, s - x).  L comes from thread x-1's slot of the previous step,
+// UL is that neighbour's value one step earlier, U is the thread's own previous pixel.  The index of
+// the pixel's residual travels along the row with the pixel (RGBA skips transparent pixels).
+// ------------------------------------------------------------------------------------------------
+constexpr int UNP_THREADS = 704;
+
+struct UnpredArgs {
+    const TileDesc* tiles;
+    const DecImage* imgs;
+    const DecTile* dt;
+    const uint8_t* in;
+    const uint32_t* resv;
+    const uint8_t* plane;     // alpha plane (RGBA)
+    const RowInfo* rows;      // RGBA: first residual index of each row
+    uint4* edge;              // strip hand-over scratch per tile row (tiles wider than UNP_THREADS)
+};
+
+template <int PXSZ>
+__device__ __forceinline__ void unpredict_tile(const UnpredArgs& A, const TileDesc& t, const DecTile* d, uint2 (*slots)[UNP_THREADS + 1]) {
+    const uint32_t tid = threadIdx.x;
+    const uint8_t* blob = A.in + d->blob_off;
+    const uint32_t* res = A.resv + t.px_off;
+    const uint8_t* pl = A.plane + t.px_off;
+    const RowInfo* rows = A.rows + t.row_off;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(t.src_off);
+    const bool grey = (d->m >> 4) == 2;
+    const uint32_t pm = grey ? (d->m & 3u) : (((d->m >> 1) & 1u) ? 3u : 2u);   // interior predictor: 0 left 1 up 2 avg2 3 grad3
+    const bool G = !grey && (d->m & 1u);
+    const uint32_t fp = ld32u(blob + 8);   // first pixel, MSB-first bits
+    uint32_t first;
+    if (grey) first = (fp >> 24) * 0x010101u;
+    else if (PXSZ == 4) first = ((fp >> 24) & 255u) | (((fp >> 16) & 255u) << 8) | (((fp >> 8) & 255u) << 16) | ((fp & 255u) << 24);
+    else first = ((fp >> 24) & 255u) | (((fp >> 16) & 255u) << 8) | (((fp >> 8) & 255u) << 16);
+    for (uint32_t xs = 0; xs < t.w; xs += UNP_THREADS) {
+        const uint32_t sw = min((uint32_t)UNP_THREADS, t.w - xs), x = xs + tid;
+        uint32_t own = 0, ownprev = 0, lprev = 0;
+        const uint32_t steps = t.h + sw - 1;
+        uint32_t rnext = 0;   // RGB: residual of my next pixel, loaded one step ahead
+        if (PXSZ == 3 && tid < sw && x) rnext = res[x - 1];
+        for (uint32_t s = 0; s < steps; s++) {
+            const uint32_t y = s - tid;
+            const bool act = tid < sw && tid <= s && y < t.h;
+            uint2 me = make_uint2(0, 0);
+            if (act) {
+                uint2 lf;
+                if (tid) lf = slots[(s + 1) & 1][tid - 1];
+                else if (xs) { const uint4 e = A.edge[t.row_off + y]; lf = make_uint2(e.x, e.y); lprev = e.z; }
+                else lf = make_uint2(0u, PXSZ == 4 ? rows[y].idx : 0u);
+                const uint32_t L = lf.x, U = own, UL = lprev;
+                uint32_t idx = lf.y, pix;
+                uint32_t rv = rnext;
+                if (PXSZ == 3 && y + 1 < t.h) rnext = res[(uint64_t)(y + 1) * t.w + x - 1];
+                if (x == 0 && y == 0) pix = first;
+                else {
+                    uint32_t a = 255;
+                    if (PXSZ == 4) a = pl[(uint64_t)y * t.w + x];
+                    if (a == 0) pix = 0;
+                    else {
+                        if (PXSZ == 4) { rv = res[idx]; idx++; }
+                        int r0 = unzz(rv & 255u), r1 = unzz((rv >> 8) & 255u), r2 = unzz((rv >> 16) & 255u);
+                        if (G && x && y) { r0 += r1; r2 += r1; }
+                        const int r[3] = { r0, r1, r2 };
+                        pix = PXSZ == 4 ? (a << 24) : 0u;
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            const int l = (L >> (8 * c)) & 255, u = (U >> (8 * c)) & 255, ul = (UL >> (8 * c)) & 255;
+                            int pd;
+                            if (y == 0) pd = l; else if (x == 0) pd = u;
+                            else pd = pm == 0 ? l : (pm == 1 ? u : (pm == 2 ? pred_avg2(l, u) : pred_grad3(l, u, ul)));
+                            pix |= (uint32_t)((r[c] + pd) & 255) << (8 * c);
+                        }
+                    }
+                }
+                uint8_t* o = dst + (uint64_t)y * t.bpr + (uint64_t)x * PXSZ;
+                if (PXSZ == 4) *reinterpret_cast<uint32_t*>(o) = pix;
+                else { o[0] = (uint8_t)pix; o[1] = (uint8_t)(pix >> 8); o[2] = (uint8_t)(pix >> 16); }
+                me = make_uint2(pix, idx);
+                lprev = L; ownprev = own; own = pix;
+                if (tid == sw - 1 && xs + sw < t.w) A.edge[t.row_off + y] = make_uint4(pix, idx, ownprev, 0);
+            }
+            slots[s & 1][tid] = me;
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(UNP_THREADS) k_dec_unpredict(UnpredArgs A) {
+    __shared__ uint2 slots[2][UNP_THREADS + 1];
+    const uint32_t tile = blockIdx.x;
+    const TileDesc t = A.tiles[tile];
+    const uint32_t mode = A.imgs[t.img].mode;
+    if (mode == 7 || (mode & 0x100)) return;
+    const DecTile* d = A.dt + tile;
+    if (d->m == 0 || d->m == 0xFE || d->m == 0xFF || ((d->m >> 4) == 2 && (d->m & 8))) return;
+    if (t.pxsz == 4) unpredict_tile<4>(A, t, d, slots);
+    else unpredict_tile<3>(A, t, d, slots);
+}
+
+// Raw grey plane (level 2, m = 0x28, libxpng.c:875-879)
+__global__ void __launch_bounds__(256) k_dec_grey_raw(const TileDesc* tiles, const DecImage* imgs, const DecTile* dt, const uint8_t* in) {
+    const uint32_t tile = blockIdx.x;
+    const TileDesc t = tiles[tile];
+    if (imgs[t.img].mode != 2) return;
+    const DecTile* d = dt + tile;
+    if ((d->m >> 4) != 2 || !(d->m & 8) || d->m == 0xFE || d->m == 0xFF) return;
+    const uint8_t* src = in + d->blob_off + 4;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(t.src_off);
+    for (uint32_t y = threadIdx.x >> 5; y < t.h; y += 8)
+        for (uint32_t x = threadIdx.x & 31; x < t.w; x += 32) {
+            const uint8_t v = src[(uint64_t)y * t.w + x];
+            uint8_t* o = dst + (uint64_t)y * t.bpr + 3ull * x;
+            o[0] = v; o[1] = v; o[2] = v;
+        }
+}
+
+}  // namespace xpb

@@ -290,6 +290,7 @@ template <int LANES>
 __global__ void __launch_bounds__(LANES) k_dec_walk(WalkArgs A) {
     __shared__ unsigned long long win[9 * LANES];
     __shared__ uint32_t rd[9 * LANES];    // symbols of stream c already moved into the window
+    __shared__ uint32_t sn[9 * LANES], so[9 * LANES];   // stream lengths / offsets
     const uint32_t tile = blockIdx.x * LANES + threadIdx.x;
     if (tile >= A.ntiles) return;
     const TileDesc t = A.tiles[tile];
@@ -299,16 +300,19 @@ __global__ void __launch_bounds__(LANES) k_dec_walk(WalkArgs A) {
     const uint8_t* sbase = A.streams + t.str_off;
     uint8_t* out = A.nlseq + t.px_off;
     auto refill = [&](uint32_t c) -> unsigned long long {
-        const uint32_t done = rd[c * LANES + threadIdx.x], n = d->blk[c].n;
+        const uint32_t done = rd[c * LANES + threadIdx.x], n = sn[c * LANES + threadIdx.x];
         if (done >= n) return 0xF0ull;   // exhausted: endless zeros (only reachable on corrupt data)
-        const unsigned long long raw = *reinterpret_cast<const unsigned long long*>(sbase + d->blk[c].soff + done);
+        const unsigned long long raw = *reinterpret_cast<const unsigned long long*>(sbase + so[c * LANES + threadIdx.x] + done);
         const uint32_t take = n - done < 8 ? n - done : 8;
         rd[c * LANES + threadIdx.x] = done + take;
         unsigned long long w = pack8_nibbles(raw);
         if (take < 8) w &= (1ull << (4 * take)) - 1;
         return w | (0xFull << (4 * take));
     };
-    for (uint32_t c = 0; c < 9; c++) { rd[c * LANES + threadIdx.x] = 0; win[c * LANES + threadIdx.x] = refill(c); }
+    for (uint32_t c = 0; c < 9; c++) {
+        rd[c * LANES + threadIdx.x] = 0; sn[c * LANES + threadIdx.x] = d->blk[c].n; so[c * LANES + threadIdx.x] = d->blk[c].soff;
+        win[c * LANES + threadIdx.x] = refill(c);
+    }
     const uint32_t m = d->nsym;
     uint32_t nl = 0, acc = 0;
     for (uint32_t i = 0; i < m; i++) {
@@ -390,184 +394,6 @@ __global__ void __launch_bounds__(256) k_dec_alpha(AlphaArgs A) {
         for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (lane == 0) A.rowcnt[t.row_off + y] = cnt;
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Row tables: for every tile row, index of its first coded pixel in nlseq and the bit offset of that
-// pixel's residual in k.  One CTA per tile: per-row bit sums (warp per row), then a serial-by-chunks scan.
-// ------------------------------------------------------------------------------------------------
-struct RowArgs {
-    const TileDesc* tiles;
-    const DecImage* imgs;
-    const DecTile* dt;
-    const uint8_t* nlseq;
-    const uint32_t* rowcnt;   // RGBA only
-    uint32_t* rowbits;        // scratch per row
-    RowInfo* rows;
-    uint32_t mode;
-};
-
-__global__ void __launch_bounds__(256) k_dec_rows(RowArgs A) {
-    const uint32_t tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const TileDesc t = A.tiles[tile];
-    if (A.imgs[t.img].mode != A.mode) return;
-    const DecTile* d = A.dt + tile;
-    if (d->m == 0 || d->m >= 0x20) return;
-    const uint64_t ro = t.row_off;
-    const uint8_t* seq = A.nlseq + t.px_off;
-    RowInfo* rows = A.rows + ro;
-    uint32_t* rb = A.rowbits + ro;
-    const bool rgba = t.pxsz == 4 && A.mode == 1;
-    // pass 1 (RGBA): exclusive scan of per-row coded counts -> rows[y].idx ; RGB: closed form
-    if (rgba) {
-        if (wid == 0) {
-            uint32_t run = 0;
-            for (uint32_t y0 = 0; y0 < t.h; y0 += 32) {
-                const uint32_t y = y0 + lane;
-                const uint32_t v = y < t.h ? A.rowcnt[ro + y] : 0;
-                uint32_t inc = v;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
-                if (y < t.h) rows[y].idx = run + inc - v;
-                run += __shfl_sync(0xffffffffu, inc, 31);
-            }
-        }
-        __syncthreads();
-    }
-    // pass 2: bits per row
-    for (uint32_t y = wid; y < t.h; y += 8) {
-        uint32_t a, b;
-        if (rgba) { a = rows[y].idx; b = a + A.rowcnt[ro + y]; }
-        else { a = y ? y * t.w - 1 : 0; b = (y + 1) * t.w - 1; }
-        uint32_t s = 0;
-        for (uint32_t k = a + lane; k < b; k += 32) s += seq[k];
-#pragma unroll
-        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) { rb[y] = 3 * s; if (!rgba) rows[y].idx = a; }
-    }
-    __syncthreads();
-    if (wid == 0) {
-        uint32_t run = (A.mode == 1 ? t.pxsz : 3u) * 8u;
-        for (uint32_t y0 = 0; y0 < t.h; y0 += 32) {
-            const uint32_t y = y0 + lane;
-            const uint32_t v = y < t.h ? rb[y] : 0;
-            uint32_t inc = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += n; }
-            if (y < t.h) rows[y].bit = run + inc - v;
-            run += __shfl_sync(0xffffffffu, inc, 31);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Un-predict (level 1).  Thread x owns column x of a strip; at step s it reconstructs pixel
-// (x, s - x).  L and UL come from thread x-1's slots of the two previous steps, U is the thread's own
-// previous pixel; the residual-bit cursor and the nlseq index travel along the row with the pixel.
-// ------------------------------------------------------------------------------------------------
-constexpr int UNP_THREADS = 704;
-
-struct UnpredArgs {
-    const TileDesc* tiles;
-    const DecImage* imgs;
-    const DecTile* dt;
-    const uint8_t* in;
-    const uint8_t* nlseq;
-    const uint8_t* plane;     // alpha plane (RGBA)
-    const RowInfo* rows;
-    uint8_t* px;              // output pixel buffer
-    uint4* edge;              // strip hand-over scratch per tile row (only tiles wider than UNP_THREADS)
-};
-
-struct Slot { uint32_t pix, bit, idx; };
-
-__device__ __forceinline__ uint32_t k_bits(const uint8_t* kb, const uint8_t* kend, uint32_t bit, uint32_t c) {
-    // c <= 24 bits starting at `bit` (MSB-first in LE words, libxpng.c:9)
-    const uint8_t* p = kb + 4ull * (bit >> 5);
-    const uint32_t w0 = (p + 4 <= kend) ? ld32u(p) : 0u, w1 = (p + 8 <= kend) ? ld32u(p + 4) : 0u;
-    const uint32_t sh = bit & 31u;
-    const uint32_t v = sh ? ((w0 << sh) | (w1 >> (32u - sh))) : w0;
-    return v >> (32u - c);
-}
-
-template <int PXSZ>
-__device__ __forceinline__ void unpredict_tile_m1(const UnpredArgs& A, const TileDesc& t, const DecTile* d, uint32_t tile,
-                                                  Slot (*slots)[UNP_THREADS + 1]) {
-    const uint32_t tid = threadIdx.x;
-    const uint8_t* blob = A.in + d->blob_off;
-    const uint8_t* kb = blob + 8; const uint8_t* kend = blob + 4 + d->bsz;
-    const uint8_t* seq = A.nlseq + t.px_off;
-    const uint8_t* pl = A.plane + t.px_off;
-    const RowInfo* rows = A.rows + t.row_off;
-    uint8_t* dst = A.px + t.src_off;
-    const bool Y = (d->m >> 1) & 1, G = d->m & 1;
-    const uint32_t fp = ld32u(kb);   // first pixel, MSB-first
-    for (uint32_t xs = 0; xs < t.w; xs += UNP_THREADS) {
-        const uint32_t sw = min((uint32_t)UNP_THREADS, t.w - xs), x = xs + tid;
-        uint32_t own = 0, ownprev = 0;     // my pixel at the previous step (= U) and the one before
-        uint32_t lprev = 0;                // left neighbour's pixel two steps ago (= UL)
-        const uint32_t steps = t.h + sw - 1;
-        for (uint32_t s = 0; s < steps; s++) {
-            const uint32_t y = s - tid;    // valid when tid <= s and y < h
-            const bool act = tid < sw && tid <= s && y < t.h;
-            Slot me{ 0, 0, 0 };
-            if (act) {
-                Slot lf;
-                if (tid) lf = slots[(s + 1) & 1][tid - 1];
-                else if (xs) { const uint4 e = A.edge[t.row_off + y]; lf = Slot{ e.x, e.y, e.z }; lprev = e.w; }
-                else { lf.pix = 0; lf.bit = rows[y].bit; lf.idx = rows[y].idx; }
-                const uint32_t L = lf.pix, U = own, UL = lprev;
-                uint32_t bit = lf.bit, idx = lf.idx, pix;
-                if (x == 0 && y == 0) {
-                    pix = PXSZ == 4 ? (((fp >> 24) & 255u) | (((fp >> 16) & 255u) << 8) | (((fp >> 8) & 255u) << 16) | ((fp & 255u) << 24))
-                                    : (((fp >> 24) & 255u) | (((fp >> 16) & 255u) << 8) | (((fp >> 8) & 255u) << 16));
-                } else {
-                    uint32_t a = 255;
-                    if (PXSZ == 4) a = pl[(uint64_t)y * t.w + x];
-                    if (a == 0) pix = 0;
-                    else {
-                        const uint32_t nl = seq[idx]; idx++;
-                        int r0 = 0, r1 = 0, r2 = 0;
-                        if (nl) {
-                            const uint32_t v = k_bits(kb, kend, bit, 3 * nl), mk = (1u << nl) - 1u;
-                            bit += 3 * nl;
-                            r0 = unzz(v >> (2 * nl)); r1 = unzz((v >> nl) & mk); r2 = unzz(v & mk);
-                        }
-                        if (G && x && y) { r0 += r1; r2 += r1; }
-                        int r[3] = { r0, r1, r2 };
-                        pix = PXSZ == 4 ? (a << 24) : 0u;
-#pragma unroll
-                        for (int c = 0; c < 3; c++) {
-                            const int l = (L >> (8 * c)) & 255, u = (U >> (8 * c)) & 255, ul = (UL >> (8 * c)) & 255;
-                            const int pd = y == 0 ? l : (x == 0 ? u : (Y ? pred_grad3(l, u, ul) : pred_avg2(l, u)));
-                            pix |= (uint32_t)((r[c] + pd) & 255) << (8 * c);
-                        }
-                    }
-                }
-                uint8_t* o = dst + (uint64_t)y * t.bpr + (uint64_t)x * PXSZ;
-                if (PXSZ == 4) *reinterpret_cast<uint32_t*>(o) = pix;
-                else { o[0] = (uint8_t)pix; o[1] = (uint8_t)(pix >> 8); o[2] = (uint8_t)(pix >> 16); }
-                me = Slot{ pix, bit, idx };
-                lprev = L;
-                ownprev = own; own = pix;
-                if (tid == sw - 1 && xs + sw < t.w) A.edge[t.row_off + y] = make_uint4(pix, bit, idx, ownprev);
-            }
-            slots[s & 1][tid] = me;
-            __syncthreads();
-        }
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(UNP_THREADS) k_dec_unpredict_m1(UnpredArgs A) {
-    __shared__ Slot slots[2][UNP_THREADS + 1];
-    const uint32_t tile = blockIdx.x;
-    const TileDesc t = A.tiles[tile];
-    if (A.imgs[t.img].mode != 1) return;
-    const DecTile* d = A.dt + tile;
-    if (d->m == 0 || d->m == 0xFE) return;
-    if (t.pxsz == 4) unpredict_tile_m1<4>(A, t, d, tile, slots);
-    else unpredict_tile_m1<3>(A, t, d, tile, slots);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -73,12 +73,12 @@ __global__ void __launch_bounds__(128) k_tile_scan(TileScanArgs A) {
     uint32_t bb = lane < 9 ? align16u(2 * len + 256) : 0, binc = bb;
 #pragma unroll
     for (int o = 1; o < 16; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, binc, o); if (lane >= o) binc += n; }
-    if (lane < 9) st->boff[lane] = binc - bb;
+    if (lane < 9) { st->boff[lane] = binc - bb; st->breg[lane] = binc - bb; }
     const uint32_t blk_total = __shfl_sync(0xffffffffu, binc, 8);
     if (MODE == 1) {
         if (lane == 9) {   // alpha stream: raster order, lives in the alpha slice
             st->len[9] = t.pxsz == 4 ? t.npx - 1 : 0; st->soff[9] = 0;
-            st->boff[9] = blk_total;
+            st->boff[9] = blk_total; st->breg[9] = blk_total;
         }
     } else {
         const uint32_t vlen = (lane >= 1 && lane < 9) ? vrun : 0, va = align16u(vlen);
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(128) k_tile_scan(TileScanArgs A) {
         for (int o = 1; o < 16; o <<= 1) { const uint32_t n = __shfl_up_sync(0xffffffffu, vbinc, o); if (lane >= o) vbinc += n; }
         if (lane >= 1 && lane < 9) {
             st->len[8 + lane] = vlen; st->soff[8 + lane] = ctx_total + vinc - va;
-            st->boff[8 + lane] = blk_total + vbinc - vb;
+            st->boff[8 + lane] = blk_total + vbinc - vb; st->breg[8 + lane] = blk_total + vbinc - vb;
         }
     }
     if (lane == 0) {
@@ -394,9 +394,37 @@ __device__ __forceinline__ bool assemble_common(const TileDesc& t, const ImageDe
     return false;
 }
 
+// One 32-bit word of a bit string that is the concatenation of `nsrc` MSB-first bit strings (sources sorted
+// by their destination bit offset sbit[]; source i contributes snb[i] bits read from the words at sptr[i]).
+__device__ __forceinline__ uint32_t gather_word(uint32_t wi, uint32_t nsrc, const uint64_t* sbit, const uint32_t* snb,
+                                                const uint32_t* const* sptr) {
+    uint64_t B = (uint64_t)wi * 32; uint32_t need = 32, word = 0;
+    uint32_t lo = 0, hi = nsrc;
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sbit[mid] <= B) lo = mid; else hi = mid; }
+    uint32_t j = lo;
+    while (need && j < nsrc) {
+        const uint64_t s0 = sbit[j]; const uint32_t nb = snb[j];
+        if (B >= s0 + nb) { j++; continue; }
+        const uint32_t loc = (uint32_t)(B - s0), avail = nb - loc, take = avail < need ? avail : need;
+        const uint32_t* sw = sptr[j];
+        const uint32_t w0 = sw[loc >> 5], sh = loc & 31;
+        const uint32_t w1 = (sh && ((loc + take - 1) >> 5) != (loc >> 5)) ? sw[(loc >> 5) + 1] : 0u;
+        const uint32_t bits32 = sh ? ((w0 << sh) | (w1 >> (32 - sh))) : w0;   // 32 bits starting at loc
+        const uint32_t got = take == 32 ? bits32 : (bits32 >> (32 - take));
+        word = take == 32 ? got : ((word << take) | got);
+        need -= take; B += take;
+    }
+    if (need) word <<= need;   // final partial word: zero padding (libxpng.c:11)
+    return word;
+}
+
+constexpr int MAX_SRC = 128;   // a tile has at most 109 segments (666 x 666 pixels / 4096) + the first pixel
+
 __global__ void __launch_bounds__(256) k_assemble_m1(AssembleArgs A) {
-    __shared__ uint64_t seg_bit[128];
-    __shared__ uint32_t seg_nb[128];
+    __shared__ uint64_t sbit[MAX_SRC];
+    __shared__ uint32_t snb[MAX_SRC];
+    __shared__ const uint32_t* sptr[MAX_SRC];
+    __shared__ uint32_t fpw;
     const uint32_t tile = blockIdx.x, tid = threadIdx.x;
     const TileDesc t = A.tiles[tile];
     const ImageDesc I = A.imgs[t.img];
@@ -413,39 +441,19 @@ __global__ void __launch_bounds__(256) k_assemble_m1(AssembleArgs A) {
     }
     const uint64_t kbits = (uint64_t)st->kbits_lo | ((uint64_t)st->kbits_hi << 32);
     const uint32_t kwords = (uint32_t)((kbits + 31) / 32);
-    if (tid == 0) { st32u(blob, (1u << 28) + (st->pr << 24) + st->size); st32u(blob + 4, 4 + 4 * kwords); }
-    for (uint32_t j = tid; j < t.nseg; j += 256) { seg_bit[j] = A.place[t.seg0 + j].bit_off; seg_nb[j] = A.seginfo[t.seg0 + j].nbits; }
-    __syncthreads();
-    // first pixel, MSB first (libxpng.c:547)
-    uint32_t fp = 0;
-    for (uint32_t c = 0; c < t.pxsz; c++) fp = (fp << 8) | src[c];
-    const uint32_t fbits = t.pxsz * 8;
-    for (uint32_t wi = tid; wi < kwords; wi += 256) {
-        uint64_t B = (uint64_t)wi * 32; uint32_t need = 32, word = 0;
-        if (B < fbits) {          // fbits is 24 or 32
-            const uint32_t take = fbits - (uint32_t)B;   // only wi == 0 gets here
-            word = fp; need -= take; B += take;
-            if (need == 0) { st32u(blob + 8 + 4ull * wi, word); continue; }
-        }
-        // segment containing bit B: last j with seg_bit[j] <= B
-        uint32_t lo = 0, hi = t.nseg;
-        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (seg_bit[mid] <= B) lo = mid; else hi = mid; }
-        uint32_t j = lo;
-        while (need && j < t.nseg) {
-            const uint64_t s0 = seg_bit[j]; const uint32_t nb = seg_nb[j];
-            if (B >= s0 + nb) { j++; continue; }
-            const uint32_t loc = (uint32_t)(B - s0), avail = nb - loc, take = avail < need ? avail : need;
-            const uint32_t* sw = reinterpret_cast<const uint32_t*>(A.bits_area + (uint64_t)(t.seg0 + j) * SEG_BITS_BYTES);
-            const uint32_t w0 = sw[loc >> 5], w1 = sw[(loc >> 5) + 1];   // area is zero-padded past nbits
-            const uint32_t sh = loc & 31;
-            const uint32_t bits32 = sh ? ((w0 << sh) | (w1 >> (32 - sh))) : w0;   // 32 bits starting at loc
-            const uint32_t got = take == 32 ? bits32 : (bits32 >> (32 - take));
-            word = take == 32 ? got : ((word << take) | got);
-            need -= take; B += take;
-        }
-        if (need) word <<= need;   // final partial word: zero padding (libxpng.c:11)
-        st32u(blob + 8 + 4ull * wi, word);
+    if (tid == 0) {
+        st32u(blob, (1u << 28) + (st->pr << 24) + st->size); st32u(blob + 4, 4 + 4 * kwords);
+        uint32_t fp = 0;            // first pixel, MSB first (libxpng.c:547), left-aligned in one word
+        for (uint32_t c = 0; c < t.pxsz; c++) fp = (fp << 8) | src[c];
+        fpw = fp << (32 - 8 * t.pxsz);
+        sbit[0] = 0; snb[0] = 8 * t.pxsz; sptr[0] = &fpw;
     }
+    for (uint32_t j = tid; j < t.nseg; j += 256) {
+        sbit[j + 1] = A.place[t.seg0 + j].bit_off; snb[j + 1] = A.seginfo[t.seg0 + j].nbits;
+        sptr[j + 1] = reinterpret_cast<const uint32_t*>(A.bits_area + (uint64_t)(t.seg0 + j) * SEG_BITS_BYTES);
+    }
+    __syncthreads();
+    for (uint32_t wi = tid; wi < kwords; wi += 256) st32u(blob + 8 + 4ull * wi, gather_word(wi, t.nseg + 1, sbit, snb, sptr));
     // entropy blocks
     uint8_t* dst = blob + 8 + 4ull * kwords;
     const uint8_t* bsrc = A.blocks + block_slice(t, tile);

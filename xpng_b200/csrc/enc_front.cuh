@@ -170,7 +170,7 @@ constexpr int HIST_CTX = 0;        // [9][16] context histograms
 constexpr int HIST_ALPHA = 256;    // [256] alpha (mode 1)
 constexpr int HIST_VAL = 256;      // mode 2: value histograms for nl = 1..8 at HIST_VAL + VAL_OFF[nl]
 constexpr int HIST_STRIDE_M1 = 512;
-constexpr int HIST_STRIDE_M2 = 256 + 576;
+constexpr int HIST_STRIDE_M2 = 1024;   // 256 ctx + 576 value bins, or 4 x 256 grey candidate bins
 
 template <int MODE, int PXSZ>
 __device__ __forceinline__ void front_segment(const FrontArgs& A, FrontShared& S, const TileDesc& t, uint32_t tile, uint32_t gseg) {
