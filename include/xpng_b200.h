@@ -66,6 +66,11 @@ int xpngb_decode(xpngb_ctx *ctx, xpngb_image *imgs, uint32_t n,
 float xpngb_last_kernel_ms(const xpngb_ctx *ctx);
 /* Number of kernel launches issued by the last call. */
 uint32_t xpngb_last_launches(const xpngb_ctx *ctx);
+/* Per-kernel timing: while on, every launch is bracketed by CUDA events and synchronised (so the call
+ * gets slower); xpngb_profile_report writes "kernel_name total_ms launches\n" lines and returns the
+ * length.  Turning profiling on or off clears the table. */
+void xpngb_profile(xpngb_ctx *ctx, int on);
+uint32_t xpngb_profile_report(const xpngb_ctx *ctx, char *buf, uint32_t cap);
 /* The CUDA stream (cudaStream_t as void*) the context launches on. */
 void *xpngb_stream(const xpngb_ctx *ctx);
 

@@ -53,6 +53,8 @@ def lib():
         L.xpngb_last_kernel_ms.restype = C.c_float; L.xpngb_last_kernel_ms.argtypes = [vp]
         L.xpngb_last_launches.restype = u32; L.xpngb_last_launches.argtypes = [vp]
         L.xpngb_stream.restype = vp; L.xpngb_stream.argtypes = [vp]
+        L.xpngb_profile.restype = None; L.xpngb_profile.argtypes = [vp, C.c_int]
+        L.xpngb_profile_report.restype = u32; L.xpngb_profile_report.argtypes = [vp, C.c_char_p, u32]
         L.xpngb_ycocg_forward.restype = C.c_int; L.xpngb_ycocg_forward.argtypes = [vp, vp, vp, u64]
         L.xpngb_ycocg_inverse.restype = C.c_int; L.xpngb_ycocg_inverse.argtypes = [vp, vp, vp, u64]
         for name in ("xpng_store", "xpng_load", "xpng_from_jpg", "xpng_store_T", "xpng_load_T", "xpng_from_jpg_T", "store_7", "load_7"):
@@ -105,6 +107,20 @@ class Codec:
     @property
     def stream(self):
         return lib().xpngb_stream(self._h)
+
+    def profile(self, on):
+        """Per-kernel CUDA-event timing (serialises launches); see profile_report()."""
+        lib().xpngb_profile(self._h, int(bool(on)))
+
+    def profile_report(self):
+        """{kernel name: (total ms, launches)} accumulated since profile(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        lib().xpngb_profile_report(self._h, buf, len(buf))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, ms, cnt = line.rsplit(" ", 2)
+            out[name] = (float(ms), int(cnt))
+        return out
 
     # ---------------------------------------------------------------- raw pointer API (bench / device-resident data)
     @staticmethod

@@ -26,7 +26,9 @@ struct xpngb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, pe0 = nullptr, pe1 = nullptr;
-    int profile = 0;   // XPNGB_PROFILE=1: per-kernel CUDA-event timing on stderr (serialises the launches)
+    int profile = 0;   // 1: per-kernel CUDA-event timing accumulated (serialises the launches); 2: also print to stderr
+    struct ProfRow { const char* name; double ms; uint32_t count; };
+    std::vector<ProfRow> prof;
     char err[512] = { 0 };
     float last_ms = 0.f;
     uint32_t launches = 0;
@@ -60,9 +62,15 @@ struct xpngb_ctx {
         if (ctx->profile) {                                                                         \
             float ms_ = 0; cudaEventRecord(ctx->pe1, ctx->stream); cudaEventSynchronize(ctx->pe1);  \
             cudaEventElapsedTime(&ms_, ctx->pe0, ctx->pe1);                                         \
-            fprintf(stderr, "[xpngb] %-28s %9.3f ms\n", #kernel, ms_);                             \
+            prof_add(ctx, #kernel, ms_);                                                            \
+            if (ctx->profile > 1) fprintf(stderr, "[xpngb] %-28s %9.3f ms\n", #kernel, ms_);       \
         }                                                                                           \
     } while (0)
+
+static void prof_add(xpngb_ctx* ctx, const char* name, float ms) {
+    for (auto& r : ctx->prof) if (!strcmp(r.name, name)) { r.ms += ms; r.count++; return; }
+    ctx->prof.push_back({ name, ms, 1 });
+}
 
 static int ensure(xpngb_ctx* ctx, DevBuf& b, size_t n) {
     n += 64;   // tail slack for vector over-reads
@@ -214,7 +222,8 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) { delete ctx; return 1; }
-    if (const char* e = getenv("XPNGB_PROFILE")) { ctx->profile = atoi(e); cudaEventCreate(&ctx->pe0); cudaEventCreate(&ctx->pe1); }
+    cudaEventCreate(&ctx->pe0); cudaEventCreate(&ctx->pe1);
+    if (const char* e = getenv("XPNGB_PROFILE")) ctx->profile = atoi(e) ? 2 : 0;
     if (const char* e = getenv("XPNGB_CHUNK_MPIX")) { const long v = atol(e); if (v > 0) ctx->max_chunk_px = (uint64_t)v << 20; }
     { auto k_big = k_rans_v2<256, 32>; cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 16); }
     m2_set_attributes();
@@ -243,6 +252,19 @@ extern "C" const char* xpngb_last_error(const xpngb_ctx* ctx) { return ctx ? ctx
 extern "C" float xpngb_last_kernel_ms(const xpngb_ctx* ctx) { return ctx ? ctx->last_ms : 0.f; }
 extern "C" uint32_t xpngb_last_launches(const xpngb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" void* xpngb_stream(const xpngb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+extern "C" void xpngb_profile(xpngb_ctx* ctx, int on) { if (ctx) { ctx->profile = on ? (ctx->profile > 1 ? 2 : 1) : 0; ctx->prof.clear(); } }
+extern "C" uint32_t xpngb_profile_report(const xpngb_ctx* ctx, char* buf, uint32_t cap) {
+    uint32_t n = 0;
+    if (!ctx || !buf || !cap) return 0;
+    buf[0] = 0;
+    for (const auto& r : ctx->prof) {
+        const int k = snprintf(buf + n, cap - n, "%s %.6f %u\n", r.name, r.ms, r.count);
+        if (k < 0 || (uint32_t)k >= cap - n) break;
+        n += (uint32_t)k;
+    }
+    return n;
+}
 
 extern "C" uint64_t xpngb_encode_bound(const xpngb_image* imgs, uint32_t n) {
     uint64_t t = 0;
