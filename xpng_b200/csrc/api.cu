@@ -597,7 +597,7 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
         for (uint32_t mode = 1; mode <= 2; mode++) {
             if (!(mode == 1 ? any1 : any2)) continue;
             WalkArgs wa{ d_tiles, d_imgs, d_dt, (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->nlseq.p, ntiles, mode };
-            LAUNCH(k_dec_walk<32>, (ntiles + 31) / 32, 32, 0, wa);
+            LAUNCH(k_dec_walk<4>, (ntiles + 3) / 4, 128, 0, wa);
         }
         ChunkArgs ch{ d_tiles, d_seg_tile, d_imgs, d_dt, (const uint8_t*)ctx->nlseq.p, (const uint8_t*)ctx->streams.p, din,
                       (uint32_t*)ctx->ccnt.p, (uint32_t*)ctx->cbit.p, (uint32_t*)ctx->resv.p, ntiles, d_err };

@@ -286,46 +286,64 @@ __device__ __forceinline__ unsigned long long pack8_nibbles(unsigned long long v
     return x;
 }
 
-template <int LANES>
-__global__ void __launch_bounds__(LANES) k_dec_walk(WalkArgs A) {
-    __shared__ unsigned long long win[9 * LANES];
-    __shared__ uint32_t rd[9 * LANES];    // symbols of stream c already moved into the window
-    __shared__ uint32_t sn[9 * LANES], so[9 * LANES];   // stream lengths / offsets
-    const uint32_t tile = blockIdx.x * LANES + threadIdx.x;
+// Warp-cooperative walk.  One warp per tile; lane c < 9 owns stream c: a 64-bit window of sixteen
+// 4-bit symbols in registers, the next sixteen prefetched.  Every lane tracks the current context
+// `nl` (uniform), so the only thing on the dependent chain is one shuffle per MACRO step: lane c
+// publishes, for its window, the length r of the leading run of self-transitions (symbols == c) and
+// the first symbol e that leaves the context; one macro step emits r copies of c followed by e.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_dec_walk(WalkArgs A) {
+    const uint32_t tile = blockIdx.x * WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (tile >= A.ntiles) return;
     const TileDesc t = A.tiles[tile];
     if (A.imgs[t.img].mode != A.mode) return;
     const DecTile* d = A.dt + tile;
     if (d->m == 0 || d->m >= 0x20) return;   // raw / grey / single colour / failed
-    const uint8_t* sbase = A.streams + t.str_off;
     uint8_t* out = A.nlseq + t.px_off;
-    auto refill = [&](uint32_t c) -> unsigned long long {
-        const uint32_t done = rd[c * LANES + threadIdx.x], n = sn[c * LANES + threadIdx.x];
-        if (done >= n) return 0xF0ull;   // exhausted: endless zeros (only reachable on corrupt data)
-        const unsigned long long raw = *reinterpret_cast<const unsigned long long*>(sbase + so[c * LANES + threadIdx.x] + done);
-        const uint32_t take = n - done < 8 ? n - done : 8;
-        rd[c * LANES + threadIdx.x] = done + take;
-        unsigned long long w = pack8_nibbles(raw);
-        if (take < 8) w &= (1ull << (4 * take)) - 1;
-        return w | (0xFull << (4 * take));
-    };
-    for (uint32_t c = 0; c < 9; c++) {
-        rd[c * LANES + threadIdx.x] = 0; sn[c * LANES + threadIdx.x] = d->blk[c].n; so[c * LANES + threadIdx.x] = d->blk[c].soff;
-        win[c * LANES + threadIdx.x] = refill(c);
-    }
     const uint32_t m = d->nsym;
-    uint32_t nl = 0, acc = 0;
-    for (uint32_t i = 0; i < m; i++) {
-        unsigned long long w = win[nl * LANES + threadIdx.x];
-        const uint32_t nx = (uint32_t)w & 0xFu;
-        w >>= 4;
-        if (w == 0xFull) w = refill(nl);
-        win[nl * LANES + threadIdx.x] = w;
-        nl = nx > 8 ? 0 : nx;
-        acc |= nl << (8 * (i & 3));
-        if ((i & 3) == 3) { *reinterpret_cast<uint32_t*>(out + i - 3) = acc; acc = 0; }
+    // per-lane stream state (lanes >= 9 own an empty stream)
+    const uint32_t c = lane < 9 ? lane : 0;
+    const uint32_t n = lane < 9 ? d->blk[c].n : 0;
+    const uint4* src = reinterpret_cast<const uint4*>(A.streams + t.str_off + d->blk[c].soff);
+    auto pack16 = [](uint4 q) -> unsigned long long {
+        const unsigned long long lo = pack8_nibbles((unsigned long long)q.x | ((unsigned long long)q.y << 32));
+        const unsigned long long hi = pack8_nibbles((unsigned long long)q.z | ((unsigned long long)q.w << 32));
+        return lo | (hi << 32);
+    };
+    uint32_t taken = 0;                      // symbols of my stream already moved into `win`
+    unsigned long long win = 0, nxt = 0; uint32_t cnt = 0;
+    if (n) { win = pack16(src[0]); cnt = n < 16 ? n : 16; taken = cnt; if (n > 16) nxt = pack16(src[1]); }
+    const unsigned long long selfpat = 0x1111111111111111ull * c;
+    auto publish = [&]() -> uint32_t {       // r | e << 5 | has_e << 9
+        if (cnt == 0) return (1u << 9);      // exhausted (corrupt data): endless zeros
+        const unsigned long long x = win ^ selfpat;
+        uint32_t r = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 2 : 16u;
+        if (r > cnt) r = cnt;
+        uint32_t info = r;
+        if (r < cnt) { uint32_t e = (uint32_t)(win >> (4 * r)) & 15u; if (e > 8) e = 0; info |= (e << 5) | (1u << 9); }
+        return info;
+    };
+    uint32_t info = publish();
+    uint32_t nl = 0, pos = 0;
+    while (pos < m) {
+        const uint32_t got = __shfl_sync(0xffffffffu, info, nl);
+        uint32_t r = got & 31u; const uint32_t has_e = (got >> 9) & 1u, e = (got >> 5) & 15u;
+        if (r + has_e > m - pos) { r = min(r, m - pos); }
+        const uint32_t k = min(r + has_e, m - pos);
+        if (lane < k) out[pos + lane] = (uint8_t)(lane < r ? nl : e);
+        if (lane == nl) {                    // pop k symbols from my window
+            if (cnt) {
+                win = k >= 16 ? 0ull : (win >> (4 * k)); cnt -= min(k, cnt);
+                if (cnt == 0 && taken < n) {
+                    win = nxt; cnt = n - taken < 16 ? n - taken : 16; taken += cnt;
+                    if (taken < n) nxt = pack16(src[taken >> 4]);
+                }
+            }
+            info = publish();
+        }
+        pos += k;
+        if (has_e) nl = e;
     }
-    if (m & 3) for (uint32_t k = 0; k < (m & 3); k++) out[(m & ~3u) + k] = (uint8_t)(acc >> (8 * k));
 }
 
 // ------------------------------------------------------------------------------------------------
