@@ -15,6 +15,7 @@
 #include "enc_m2.cuh"
 #include "dec_m1.cuh"
 #include "dec_back.cuh"
+#include "dec_rans_lat.cuh"
 #include "misc.cuh"
 
 using namespace xpb;
@@ -33,6 +34,7 @@ struct xpngb_ctx {
     float last_ms = 0.f;
     uint32_t launches = 0;
     uint64_t max_chunk_px = 1ull << 30;
+    uint32_t lat_max_blocks = 8192;   // entropy blocks per launch up to which the warp-per-block (latency) kernels are used
     // device scratch
     DevBuf pixels, norm, files, arena, tiles, imgs, seg_tile, costs, hist, seginfo, place, vplace, vcnt, sym_area,
         bits_area, alpha, streams, blocks, state, outs, flags, skip, dimgs, dtiles, plane, nlseq, rowcnt, rowbits,
@@ -166,6 +168,9 @@ static int upload_plan(xpngb_ctx* ctx, const Plan& P) {
 // ------------------------------------------------------------------------------------------------
 // Level 2 host side
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t LAT_LUT_V2 = 1024 + 32768, LAT_SMEM_V2 = LAT_CUM_WORDS * 4 + LAT_LUT_V2 + LAT_RING * 4;   // 2^12 x 4 B direct table or byte table 2^15 + 1 KiB
+constexpr uint32_t LAT_LUT_V1 = 65536, LAT_SMEM_V1 = LAT_CUM_WORDS * 4 + LAT_LUT_V1 + LAT_RING * 4;          // 2^14 x 4 B direct table
+
 static void m2_set_attributes() {
     auto k_big = k_rans_v1<256, 32>;
     cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 16);
@@ -227,6 +232,8 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     if (const char* e = getenv("XPNGB_CHUNK_MPIX")) { const long v = atol(e); if (v > 0) ctx->max_chunk_px = (uint64_t)v << 20; }
     { auto k_big = k_rans_v2<256, 32>; cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 16); }
     m2_set_attributes();
+    if (const char* e = getenv("XPNGB_LAT_MAX_BLOCKS")) ctx->lat_max_blocks = (uint32_t)atol(e);
+    cudaFuncSetAttribute(k_dec_rans_v1_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, LAT_SMEM_V1);
     *out = ctx;
     return 0;
 }
@@ -573,9 +580,12 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
     if (any1) {
         LAUNCH(k_dec_parse_m1, (ntiles + 127) / 128, 128, 0, d_tiles, d_imgs, din, d_dt, ntiles, d_err);
         RansDecArgs ra{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, (uint8_t*)ctx->alpha.p, ntiles, 0, 9 };
-        LAUNCH(k_dec_rans_v2_small<128>, (9 * ntiles + 127) / 128, 128, 0, ra);
+        const bool lat = 9 * ntiles <= ctx->lat_max_blocks;
+        if (lat) LAUNCH(k_dec_rans_v2_lat, 9 * ntiles, 32, LAT_SMEM_V2, ra, LAT_LUT_V2);
+        else LAUNCH(k_dec_rans_v2_small<128>, (9 * ntiles + 127) / 128, 128, 0, ra);
         if (P.any_rgba) {
-            LAUNCH(k_dec_rans_v2_big<32>, (ntiles + 31) / 32, 32, 32 * 258 * 2 + 32 * 260, ra);
+            if (lat) { ra.c0 = 9; ra.nc = 1; LAUNCH(k_dec_rans_v2_lat, ntiles, 32, LAT_SMEM_V2, ra, LAT_LUT_V2); }
+            else LAUNCH(k_dec_rans_v2_big<32>, (ntiles + 31) / 32, 32, 32 * 258 * 2 + 32 * 260, ra);
             AlphaArgs al{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->alpha.p, (uint8_t*)ctx->plane.p, (uint32_t*)ctx->rowcnt.p };
             LAUNCH(k_dec_alpha, ntiles, 256, 0, al);
             LAUNCH(k_dec_rows_rgba, ntiles, 32, 0, d_tiles, d_imgs, (const DecTile*)d_dt, (const uint32_t*)ctx->rowcnt.p, (RowInfo*)ctx->rows.p);
@@ -583,6 +593,10 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
     }
     if (any2) {
         LAUNCH(k_dec_parse_m2, (ntiles + 127) / 128, 128, 0, d_tiles, d_imgs, din, d_dt, ntiles, d_err);
+        if (17 * ntiles <= ctx->lat_max_blocks) {
+            RansV1LatArgs la{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 17, LAT_LUT_V1 };
+            LAUNCH(k_dec_rans_v1_lat, 17 * ntiles, 32, LAT_SMEM_V1, la);
+        } else {
         RansV1DecArgs rv{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 9, 0, 16 };
         auto k8 = k_dec_rans_v1_small<8, 128>; auto k15 = k_dec_rans_v1_small<15, 128>; auto kbig = k_dec_rans_v1_big<32>;
         LAUNCH(k8, (9 * ntiles + 127) / 128, 128, 0, rv);                     // contexts (9 symbols); grey tiles: nothing (N = 256)
@@ -592,12 +606,14 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
         LAUNCH(kbig, (8 * ntiles + 31) / 32, 32, 32 * 258 * 2 + 32 * 260, rv); // value alphabets of 32..256 symbols
         rv.c0 = 0; rv.nc = 1;
         LAUNCH(kbig, (ntiles + 31) / 32, 32, 32 * 258 * 2 + 32 * 260, rv);     // grey planes
+        }
     }
     if (any1 || any2) {
         for (uint32_t mode = 1; mode <= 2; mode++) {
             if (!(mode == 1 ? any1 : any2)) continue;
             WalkArgs wa{ d_tiles, d_imgs, d_dt, (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->nlseq.p, ntiles, mode };
-            LAUNCH(k_dec_walk<4>, (ntiles + 3) / 4, 128, 0, wa);
+            if (ntiles <= 592) LAUNCH(k_dec_walk_lat<1>, ntiles, 32, 0, wa);
+            else LAUNCH(k_dec_walk_lat<4>, (ntiles + 3) / 4, 128, 0, wa);
         }
         ChunkArgs ch{ d_tiles, d_seg_tile, d_imgs, d_dt, (const uint8_t*)ctx->nlseq.p, (const uint8_t*)ctx->streams.p, din,
                       (uint32_t*)ctx->ccnt.p, (uint32_t*)ctx->cbit.p, (uint32_t*)ctx->resv.p, ntiles, d_err };

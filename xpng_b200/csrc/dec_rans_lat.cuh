@@ -1,0 +1,315 @@
+// dec_rans_lat.cuh — latency-optimised rANS block decoders (v2: libxpng.c:429-493, v1: :262-301).
+//
+// The two rANS states of a block share one word pointer, so a block is ONE serial chain; with few
+// blocks in flight (a single frame has 45 tiles x 9..17 blocks) the GPU is latency-bound and the only
+// thing that matters is the length of the dependent instruction chain per symbol.  These kernels give
+// every block a whole warp and a direct slot -> (symbol, freq, slot - start) table in shared memory:
+//     slot = x & mask                       LOP      4 cycles
+//     e    = lut[slot]                      LDS     23 cycles
+//     x    = f * (x >> pb) + bias           IMAD.WIDE + IMAD
+//     x    = x < 2^31 ? x << 32 | w : x     SHF, ISETP, SEL (branch-free; the word pointer moves by the predicate)
+// All 32 lanes execute the chain redundantly (warp-uniform, broadcast loads); lane 0 stores.  The lanes
+// cooperate on everything that is parallel: table construction, run (type 1) and raw (type 2) blocks.
+// Alphabets above 16 symbols (or PROB_BITS 15) use a byte table slot -> symbol plus a 256-entry
+// (freq, start) table: two dependent shared loads per symbol.
+// The lane-per-block kernels in dec_m1.cuh / dec_back.cuh remain the throughput variant for large batches.
+#pragma once
+#include "common.cuh"
+#include "dec_m1.cuh"
+#include "dec_back.cuh"
+
+namespace xpb {
+
+// Renormalisation words are staged through a shared-memory ring by the whole warp (bulk, coalesced,
+// misalignment removed with a funnel shift, zeros past the end: libxpng.c:295, :475), so that the
+// chain reads them with fixed-latency shared loads issued one step ahead of their use.
+constexpr uint32_t LAT_RING = 2048;              // words; refilled in halves
+constexpr uint32_t LAT_HALF = LAT_RING / 2;
+
+template <int DIR>
+struct WordSrc {
+    const uint32_t* base;   // 4-aligned address at or below word 0
+    uint32_t sh;            // 8 * misalignment
+    uint32_t nwords;        // words available
+    uint32_t jmax;          // forward: highest aligned index that may be touched
+    // first = address of word 0; DIR = +1: words at first + 4k; DIR = -1: words at first - 4k.
+    // Backward sources are followed by the block's two states, so base - k + 1 is always inside the block.
+    __device__ __forceinline__ void init(const uint8_t* first, uint32_t n) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(first);
+        base = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        sh = (uint32_t)(a & 3u) * 8u;
+        nwords = n;
+        jmax = sh ? n : (n ? n - 1 : 0);
+    }
+    // Stage words [k0, k0 + LAT_HALF) into ring slots (k0 .. ) mod LAT_RING.  All lanes.
+    __device__ __forceinline__ void stage(uint32_t* ring, uint32_t k0, uint32_t lane) const {
+        for (uint32_t k = k0 + lane; k < k0 + LAT_HALF; k += 32) {
+            uint32_t v = 0;
+            if (k < nwords) {
+                uint32_t a0, a1;
+                if (DIR > 0) { a0 = __ldg(base + k); a1 = __ldg(base + min(k + 1, jmax)); }
+                else { a0 = __ldg(base - k); a1 = __ldg(base - k + 1); }
+                v = __funnelshift_r(a0, a1, sh);
+            }
+            ring[k & (LAT_RING - 1)] = v;
+        }
+    }
+};
+
+// Build the direct table for alphabets of at most 16 symbols: entry = bias | freq << 14 | sym << 28.
+__device__ __forceinline__ void lat_build_lut1(uint32_t* lut, const uint32_t* cum, uint32_t N, int pb, uint32_t lane) {
+    const uint32_t total = 1u << pb;
+    for (uint32_t s = 0; s < N; s++) {
+        const uint32_t c0 = min(cum[s], total), c1 = min(cum[s + 1], total), f = c1 - c0;
+        for (uint32_t i = c0 + lane; i < c1; i += 32) lut[i] = (i - c0) | (f << 14) | (s << 28);
+    }
+    for (uint32_t i = min(cum[N], total) + lane; i < total; i += 32) lut[i] = 0;   // corrupt table: uncovered slots
+}
+// Two-level tables: sym8[slot] and tab[sym] = start | freq << 16.
+__device__ __forceinline__ void lat_build_lut2(uint8_t* sym8, uint32_t* tab, const uint32_t* cum, uint32_t N, int pb, uint32_t lane) {
+    const uint32_t total = 1u << pb;
+    for (uint32_t s = lane; s < 256; s += 32) {
+        const uint32_t c0 = s < N ? min(cum[s], total) : total, c1 = s < N ? min(cum[s + 1], total) : total;
+        tab[s] = (c0 & 0xFFFFu) | ((c1 - c0) << 16);
+    }
+    for (uint32_t s = 0; s < N; s++) {
+        const uint32_t c0 = min(cum[s], total), c1 = min(cum[s + 1], total);
+        for (uint32_t i = c0 + lane; i < c1; i += 32) sym8[i] = (uint8_t)s;
+    }
+    for (uint32_t i = min(cum[N], total) + lane; i < total; i += 32) sym8[i] = 0;
+}
+
+// The chain.  DIR = +1: symbols 0..n-1 in order (v1); DIR = -1: symbols n-1..0 (v2).  Symbol i uses
+// state (i & 1).  Output bytes go to out[i]; lane 0 stores four at a time.  CLAMP: symbols above 8 are
+// stored as 0 (context streams: the walk indexes lanes by them).
+template <int DIR, bool TWO, bool CLAMP>
+__device__ __forceinline__ void lat_chain(const uint32_t* lut, const uint8_t* sym8, const uint32_t* tab, uint32_t* ring, const int pb, uint64_t x0,
+                                          uint64_t x1, const WordSrc<DIR>& ws, uint8_t* out, const uint32_t n, const uint32_t lane) {
+    const uint32_t mask = (1u << pb) - 1u;
+    ws.stage(ring, 0, lane); ws.stage(ring, LAT_HALF, lane);
+    __syncwarp();
+    uint32_t k = 0, loaded = LAT_RING;             // words consumed / staged
+    uint32_t lo = ring[0], hi = ring[1];           // ring[k], ring[k + 1] as of the previous step
+    bool pp = false;                                // previous step renormalised
+    auto step = [&](uint64_t& x) -> uint32_t {
+        const uint32_t w = pp ? hi : lo;            // = ring[k]
+        lo = ring[k & (LAT_RING - 1)]; hi = ring[(k + 1) & (LAT_RING - 1)];   // for the next step
+        const uint32_t slot = (uint32_t)x & mask;
+        uint32_t f, bias, s;
+        if (TWO) { s = sym8[slot]; const uint32_t e = tab[s]; f = e >> 16; bias = slot - (e & 0xFFFFu); }
+        else { const uint32_t e = lut[slot]; f = (e >> 14) & 0x3FFFu; bias = e & 0x3FFFu; s = e >> 28; }
+        x = (uint64_t)f * (x >> pb) + bias;
+        const bool p = x < (1ull << 31);
+        x = p ? ((x << 32) | w) : x;
+        k += p ? 1u : 0u; pp = p;
+        if (CLAMP) s = s > 8u ? 0u : s;
+        return s;
+    };
+    auto top_up = [&]() {                           // warp-uniform: k is the same in every lane
+        if (k + LAT_HALF >= loaded) { __syncwarp(); ws.stage(ring, loaded, lane); loaded += LAT_HALF; __syncwarp(); }
+    };
+    if (DIR > 0) {
+        uint32_t i = 0;
+        for (; i + 4 <= n; i += 4) {
+            const uint32_t s0 = step(x0), s1 = step(x1), s2 = step(x0), s3 = step(x1);
+            if (lane == 0) *reinterpret_cast<uint32_t*>(out + i) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+            top_up();
+        }
+        for (; i < n; i++) { const uint32_t s = (i & 1) ? step(x1) : step(x0); if (lane == 0) out[i] = (uint8_t)s; }
+    } else {
+        uint32_t i = n;                              // symbols left; next to decode is i - 1
+        for (; i && (i & 3); i--) { const uint32_t s = ((i - 1) & 1) ? step(x1) : step(x0); if (lane == 0) out[i - 1] = (uint8_t)s; }
+        for (; i >= 4; i -= 4) {
+            const uint32_t s3 = step(x1), s2 = step(x0), s1 = step(x1), s0 = step(x0);
+            if (lane == 0) *reinterpret_cast<uint32_t*>(out + i - 4) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+            top_up();
+        }
+    }
+}
+
+// Parallel fills for the trivial block types.
+__device__ __forceinline__ void lat_fill_run(uint8_t* out, uint32_t n, uint32_t sym, uint32_t lane) {
+    const uint32_t v4 = sym * 0x01010101u;
+    for (uint32_t k = lane; k < (n + 3) / 4; k += 32) reinterpret_cast<uint32_t*>(out)[k] = v4;
+}
+__device__ __forceinline__ void lat_fill_raw(uint8_t* out, uint32_t n, uint32_t nbit, const uint8_t* bits, const uint8_t* end, uint32_t bit0, uint32_t lane,
+                                             bool clamp) {
+    for (uint32_t k = lane; k < n; k += 32) {
+        BitR r{ bits, end, bit0 + k * nbit };
+        uint32_t v = r.get(nbit); if (clamp && v > 8u) v = 0;
+        out[k] = (uint8_t)v;
+    }
+}
+
+// Frequency table -> cum[0..N] in shared memory (lane 0; type 4 tables are a serial bit scan).
+__device__ __forceinline__ void lat_read_table(uint32_t* cum, const uint8_t* bits, const uint8_t* end, uint32_t bit0, uint32_t N, int pb, bool sparse,
+                                               uint32_t lane) {
+    if (!sparse) {   // fixed-width entries: parallel read, then a serial prefix (N <= 256)
+        for (uint32_t i = lane; i < N; i += 32) { BitR r{ bits, end, bit0 + i * (uint32_t)pb }; cum[i + 1] = r.get((uint32_t)pb); }
+        __syncwarp();
+        if (lane == 0) { cum[0] = 0; uint32_t acc = 0; for (uint32_t i = 0; i < N; i++) { acc += cum[i + 1]; cum[i + 1] = acc; } }
+    } else if (lane == 0) {
+        BitR r{ bits, end, bit0 };
+        uint32_t acc = 0; cum[0] = 0;
+        for (uint32_t i = 0; i < N; i++) { if (r.get(1)) acc += r.get((uint32_t)pb); cum[i + 1] = acc; }
+    }
+    __syncwarp();
+}
+
+constexpr uint32_t LAT_CUM_WORDS = 260;   // cum[257] + pad, at the start of dynamic shared memory
+
+// ---------------------------------------------------------------------------------------------------
+// v2 blocks (level 1).  One warp (= one CTA) per block; id = j * ntiles + tile with c = c0 + j.
+// lut_bytes = dynamic shared memory behind cum[] available for tables.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) k_dec_rans_v2_lat(RansDecArgs A, uint32_t lut_bytes) {
+    extern __shared__ __align__(16) uint32_t lat_smem[];
+    uint32_t* cum = lat_smem;
+    uint32_t* lut = lat_smem + LAT_CUM_WORDS;
+    const uint32_t id = blockIdx.x, lane = threadIdx.x;
+    const uint32_t c = A.c0 + id / A.ntiles, tile = id % A.ntiles;
+    const TileDesc t = A.tiles[tile];
+    if (A.imgs[t.img].mode != 1) return;
+    if (c == 9 && t.pxsz != 4) return;
+    const DecTile* d = A.dt + tile;
+    if (d->m == 0 || d->m == 0xFE) return;
+    const DecBlock b = d->blk[c];
+    const uint8_t* blk = A.in + d->blob_off + b.off;
+    uint8_t* out = c == 9 ? A.alpha + t.px_off : A.streams + t.str_off + b.soff;
+    const uint32_t n = b.n;
+    if (b.type == 0 || n == 0) return;
+    const uint32_t w1 = ld32u(blk + 4), v2 = w1 >> 24, csz = ld32u(blk) & 0xFFFFFFu;
+    const bool ctx = c < 9;
+    if (b.type == 1) { lat_fill_run(out, n, ctx && v2 > 8u ? 0u : v2, lane); return; }
+    if (b.type == 2) { lat_fill_raw(out, n, v2, blk + 8, blk + csz, 0, lane, ctx); return; }
+    const uint32_t N = v2 + 2, w2 = ld32u(blk + 8); const int pb = (int)(w2 >> 24);
+    const uint32_t tabw = w2 & 0xFFFFFFu;
+    const bool two = N > 16 || (4u << pb) > lut_bytes;
+    if (N > 256 || pb < 10 || pb > 15 || 8 + 4ull * tabw > csz || tabw < 5 || (two && (1u << pb) + 1024u > lut_bytes)) {
+        for (uint32_t k = lane; k < n; k += 32) out[k] = 0;
+        return;
+    }
+    const uint8_t* tab = blk + 8 + 4ull * tabw;
+    lat_read_table(cum, tab, blk + csz, 0, N, pb, b.type == 4, lane);
+    uint32_t* tab2 = lut; uint8_t* sym8 = reinterpret_cast<uint8_t*>(lut + 256);
+    if (two) lat_build_lut2(sym8, tab2, cum, N, pb, lane); else lat_build_lut1(lut, cum, N, pb, lane);
+    __syncwarp();
+    const uint8_t* sp = tab - 16;                       // state0, state1 (libxpng.c:467)
+    const uint64_t x0 = ld64u(sp), x1 = ld64u(sp + 8);
+    WordSrc<-1> ws; ws.init(sp - 4, (uint32_t)((sp - (blk + 12)) / 4));
+    uint32_t* ring = lut + lut_bytes / 4;
+    if (two) lat_chain<-1, true, false>(nullptr, sym8, tab2, ring, pb, x0, x1, ws, out, n, lane);
+    else if (ctx) lat_chain<-1, false, true>(lut, nullptr, nullptr, ring, pb, x0, x1, ws, out, n, lane);
+    else lat_chain<-1, false, false>(lut, nullptr, nullptr, ring, pb, x0, x1, ws, out, n, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// v1 blocks (level 2; libxpng.c:262-301).  Block order: long value streams first, so that the longest
+// chains start in the first wave of CTAs.
+// ---------------------------------------------------------------------------------------------------
+__device__ __constant__ const uint8_t LAT_M2_ORDER[17] = { 12, 13, 11, 14, 15, 16, 0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 9 };
+
+struct RansV1LatArgs {
+    const TileDesc* tiles;
+    const DecImage* imgs;
+    const DecTile* dt;
+    const uint8_t* in;
+    uint8_t* streams;
+    uint32_t ntiles;
+    uint32_t j0, nj;        // range of LAT_M2_ORDER handled by this launch
+    uint32_t lut_bytes;
+};
+
+__global__ void __launch_bounds__(32) k_dec_rans_v1_lat(RansV1LatArgs A) {
+    extern __shared__ __align__(16) uint32_t lat_smem[];
+    uint32_t* cum = lat_smem;
+    uint32_t* lut = lat_smem + LAT_CUM_WORDS;
+    const uint32_t id = blockIdx.x, lane = threadIdx.x;
+    const uint32_t c = LAT_M2_ORDER[A.j0 + id / A.ntiles], tile = id % A.ntiles;
+    const TileDesc t = A.tiles[tile];
+    if (A.imgs[t.img].mode != 2) return;
+    const DecTile* d = A.dt + tile;
+    const uint32_t kind = d->m >> 4;
+    if (d->m == 0xFE || d->m == 0xFF || d->m == 0 || (kind == 2 && (d->m & 8))) return;
+    const bool grey = kind == 2;
+    if (grey && c != 0) return;
+    const uint32_t N = grey ? 256u : (uint32_t)DEC_M2_NSYM[c]; const int pb = grey ? 15 : 14;
+    const DecBlock b = d->blk[c];
+    const uint8_t* blob = A.in + d->blob_off; const uint8_t* blk = blob + b.off;
+    uint8_t* out = A.streams + t.str_off + b.soff;
+    const uint32_t n = b.n;
+    if (b.type == 0 || n == 0) return;
+    const uint8_t* side = blob + 8; const uint8_t* side_end = blob + 4 + d->bsz;
+    const uint32_t bitpos = d->bitpos[c];
+    const bool ctx = !grey && c < 9;
+    if (b.type == 1) { const uint32_t v = ld32u(blk + 4) >> 24; lat_fill_run(out, n, ctx && v > 8u ? 0u : v, lane); return; }
+    if (b.type == 2) { lat_fill_raw(out, n, bitlen32(N - 1), side, side_end, bitpos, lane, ctx); return; }
+    const uint32_t bsize = ld32u(blk) & 0xFFFFFFu;
+    const bool two = N > 16 || (4u << pb) > A.lut_bytes;
+    if (two && (1u << pb) + 1024u > A.lut_bytes) { for (uint32_t k = lane; k < n; k += 32) out[k] = 0; return; }
+    lat_read_table(cum, side, side_end, bitpos, N, pb, b.type == 4, lane);
+    uint32_t* tab2 = lut; uint8_t* sym8 = reinterpret_cast<uint8_t*>(lut + 256);
+    if (two) lat_build_lut2(sym8, tab2, cum, N, pb, lane); else lat_build_lut1(lut, cum, N, pb, lane);
+    __syncwarp();
+    const uint64_t x0 = ld64u(blk + 8), x1 = ld64u(blk + 16);
+    WordSrc<1> ws; ws.init(blk + 24, bsize >= 24 ? (bsize - 24) / 4 : 0u);
+    uint32_t* ring = lut + A.lut_bytes / 4;
+    if (two) lat_chain<1, true, false>(nullptr, sym8, tab2, ring, pb, x0, x1, ws, out, n, lane);
+    else if (ctx) lat_chain<1, false, true>(lut, nullptr, nullptr, ring, pb, x0, x1, ws, out, n, lane);
+    else lat_chain<1, false, false>(lut, nullptr, nullptr, ring, pb, x0, x1, ws, out, n, lane);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Context walk, latency variant (nl_{i+1} = next unread symbol of stream nl_i, libxpng.c:803).
+// One warp per tile, lane c < 9 owns stream c (64-bit register window of eight byte symbols, the next
+// eight prefetched).  Every lane publishes the head of its stream in `info`; the whole dependent chain
+// is ONE shuffle per symbol: got = shfl(info, cur) with cur = the previous got.  The owner pops its
+// window while the shuffle is in flight (the pop depends on cur only), so self-transitions cost nothing
+// extra.  Lane j of each group of 32 steps keeps symbol j; one coalesced store per 32 symbols.
+// ---------------------------------------------------------------------------------------------------
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_dec_walk_lat(WalkArgs A) {
+    const uint32_t tile = blockIdx.x * WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (tile >= A.ntiles) return;
+    const TileDesc t = A.tiles[tile];
+    if (A.imgs[t.img].mode != A.mode) return;
+    const DecTile* d = A.dt + tile;
+    if (d->m == 0 || d->m >= 0x20) return;   // raw / grey / single colour / failed
+    uint8_t* out = A.nlseq + t.px_off;
+    const uint32_t m = d->nsym;
+    const uint32_t c = lane < 9 ? lane : 0;
+    const uint32_t nch = lane < 9 ? (d->blk[c].n + 7) / 8 : 0;   // 8-symbol chunks of my stream (symbols are <= 8 by construction)
+    const uint2* src = reinterpret_cast<const uint2*>(A.streams + t.str_off + d->blk[c].soff);
+    uint32_t wlo = 0, whi = 0, nlo = 0, nhi = 0;                 // window and the prefetched next chunk
+    if (nch > 0) { const uint2 q = __ldg(src); wlo = q.x; whi = q.y; }
+    if (nch > 1) { const uint2 q = __ldg(src + 1); nlo = q.x; nhi = q.y; }
+    uint32_t ch = 2, cnt = 8;
+    uint32_t info = wlo & 0xFFu;
+    uint32_t cur = 0;
+    for (uint32_t pos = 0; pos < m; pos += 32) {
+        uint32_t keep = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const uint32_t got = __shfl_sync(0xffffffffu, info, cur);
+            // everything below depends on cur only and overlaps the shuffle
+            const bool own = lane == cur;
+            const bool ref = own && cnt == 1u;
+            const uint32_t plo = __funnelshift_r(wlo, whi, 8), phi = whi >> 8;
+            wlo = own ? plo : wlo; whi = own ? phi : whi; cnt -= own ? 1u : 0u;
+            if (__any_sync(0xffffffffu, ref)) {                  // warp-uniform branch, about once per 8 steps
+                wlo = ref ? nlo : wlo; whi = ref ? nhi : whi; cnt = ref ? 8u : cnt;
+                const uint32_t doload = (ref && ch < nch) ? 1u : 0u;
+                nlo = ref ? 0u : nlo; nhi = ref ? 0u : nhi;
+                asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %3, 0;\n @q ld.global.nc.v2.u32 {%0, %1}, [%2];\n}"
+                             : "+r"(nlo), "+r"(nhi) : "l"(src + ch), "r"(doload));
+                ch += ref ? 1u : 0u;
+            }
+            info = wlo & 0xFFu;
+            keep = lane == (uint32_t)j ? got : keep;
+            cur = got;
+        }
+        if (pos + lane < m) out[pos + lane] = (uint8_t)keep;
+    }
+}
+
+}  // namespace xpb
