@@ -13,6 +13,7 @@
 #include "enc_front.cuh"
 #include "enc_back.cuh"
 #include "enc_m2.cuh"
+#include "enc_rans_lat.cuh"
 #include "dec_m1.cuh"
 #include "dec_back.cuh"
 #include "dec_rans_lat.cuh"
@@ -168,8 +169,8 @@ static int upload_plan(xpngb_ctx* ctx, const Plan& P) {
 // ------------------------------------------------------------------------------------------------
 // Level 2 host side
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t LAT_LUT_V2 = 1024 + 32768, LAT_SMEM_V2 = LAT_CUM_WORDS * 4 + LAT_LUT_V2 + LAT_RING * 4;   // 2^12 x 4 B direct table or byte table 2^15 + 1 KiB
-constexpr uint32_t LAT_LUT_V1 = 65536, LAT_SMEM_V1 = LAT_CUM_WORDS * 4 + LAT_LUT_V1 + LAT_RING * 4;          // 2^14 x 4 B direct table
+constexpr uint32_t LAT_LUT_V2 = 1024 + 32768, LAT_SMEM_V2 = LAT_CUM_WORDS * 4 + LAT_LUT_V2 + LAT_RING_WORDS * 4;   // 2^12 x 4 B direct table or byte table 2^15 + 1 KiB
+constexpr uint32_t LAT_LUT_V1 = 65536, LAT_SMEM_V1 = LAT_CUM_WORDS * 4 + LAT_LUT_V1 + LAT_RING_WORDS * 4;          // 2^14 x 4 B direct table
 
 static void m2_set_attributes() {
     auto k_big = k_rans_v1<256, 32>;
@@ -199,12 +200,21 @@ static int m2_encode_tiles(xpngb_ctx* ctx, const Plan& P, uint32_t ntiles, uint3
     LAUNCH(k_m2_grey_front, nseg, 256, 0, d_tiles, d_seg_tile, (const uint8_t*)ctx->tclass.p, (uint8_t*)ctx->streams.p, (uint32_t*)ctx->hist.p);
     RansV1Args ra{ d_tiles, (TileState*)ctx->state.p, (const uint32_t*)ctx->hist.p, (const uint8_t*)ctx->tclass.p,
                    (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->blocks.p, (uint32_t*)ctx->tabs.p, ntiles, 0, 17, 0, 0 };
+    if (17 * ntiles <= ctx->lat_max_blocks) {
+        auto p_small = k_rans_v1_pair<16>; auto p_big = k_rans_v1_pair<256>;
+        LAUNCH(p_small, (17 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 16 * PAIR_BLK * 16, ra);
+        ra.c0 = 9; ra.nc = 8; ra.nmin = 16;
+        LAUNCH(p_big, (8 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 256 * PAIR_BLK * 16, ra);
+        ra.c0 = 0; ra.nc = 4; ra.nmin = 0; ra.grey = 1;
+        LAUNCH(p_big, (4 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 256 * PAIR_BLK * 16, ra);
+    } else {
     auto k_small = k_rans_v1<16, 128>; auto k_big = k_rans_v1<256, 32>;
     LAUNCH(k_small, (17 * ntiles + 127) / 128, 128, 16 * 128 * 16, ra);
     ra.c0 = 9; ra.nc = 8; ra.nmin = 16;
     LAUNCH(k_big, (8 * ntiles + 31) / 32, 32, 256 * 32 * 16, ra);
     ra.c0 = 0; ra.nc = 4; ra.nmin = 0; ra.grey = 1;
     LAUNCH(k_big, (4 * ntiles + 31) / 32, 32, 256 * 32 * 16, ra);
+    }
     LAUNCH(k_m2_finish, (ntiles + 127) / 128, 128, 0, d_tiles, (const uint8_t*)ctx->tclass.p, (TileState*)ctx->state.p, ntiles);
     return 0;
 }
@@ -233,6 +243,9 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     { auto k_big = k_rans_v2<256, 32>; cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 16); }
     m2_set_attributes();
     if (const char* e = getenv("XPNGB_LAT_MAX_BLOCKS")) ctx->lat_max_blocks = (uint32_t)atol(e);
+    { auto p = k_rans_v2_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * PAIR_BLK * 16); }
+    { auto p = k_rans_v1_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * PAIR_BLK * 16); }
+    cudaFuncSetAttribute(k_dec_walk_smem<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WALK_SMEM_MAX_SYMS / 8 + 32) * 4);
     cudaFuncSetAttribute(k_dec_rans_v1_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, LAT_SMEM_V1);
     *out = ctx;
     return 0;
@@ -393,11 +406,17 @@ static int encode_chunk(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32_t n
         LAUNCH(k_compact<1>, nseg, 256, 0, ca);
         RansV2Args ra{ d_tiles, (TileState*)ctx->state.p, (uint32_t*)ctx->hist.p, (const uint8_t*)ctx->streams.p,
                        (const uint8_t*)ctx->alpha.p, (uint8_t*)ctx->blocks.p, ntiles, 0, 9 };
+        if (9 * ntiles <= ctx->lat_max_blocks) {
+            auto p_small = k_rans_v2_pair<16>; auto p_big = k_rans_v2_pair<256>;
+            LAUNCH(p_small, (9 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 16 * PAIR_BLK * 16, ra);
+            if (P.any_rgba) { ra.c0 = 9; ra.nc = 1; LAUNCH(p_big, (ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 256 * PAIR_BLK * 16, ra); }
+        } else {
         auto k_small = k_rans_v2<9, 128>; auto k_big = k_rans_v2<256, 32>;
         LAUNCH(k_small, (9 * ntiles + 127) / 128, 128, 9 * 128 * 16, ra);
         if (P.any_rgba) {
             ra.c0 = 9; ra.nc = 1;
             LAUNCH(k_big, (ntiles + 31) / 32, 32, 256 * 32 * 16, ra);
+        }
         }
     }
     if (any2) {
@@ -612,7 +631,11 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
         for (uint32_t mode = 1; mode <= 2; mode++) {
             if (!(mode == 1 ? any1 : any2)) continue;
             WalkArgs wa{ d_tiles, d_imgs, d_dt, (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->nlseq.p, ntiles, mode };
-            if (ntiles <= 592) LAUNCH(k_dec_walk_lat<1>, ntiles, 32, 0, wa);
+            uint32_t maxpx = 0;
+            for (const TileDesc& t : P.tiles) if (t.npx > maxpx) maxpx = t.npx;
+            const uint32_t wsm = (maxpx / 8 + 32) * 4;          // nibble-packed streams of the largest tile + pad words
+            if (ntiles <= 592 && maxpx <= WALK_SMEM_MAX_SYMS) LAUNCH(k_dec_walk_smem<0>, ntiles, 32, wsm, wa);
+            else if (ntiles <= 592) LAUNCH(k_dec_walk_lat<1>, ntiles, 32, 0, wa);
             else LAUNCH(k_dec_walk_lat<4>, (ntiles + 3) / 4, 128, 0, wa);
         }
         ChunkArgs ch{ d_tiles, d_seg_tile, d_imgs, d_dt, (const uint8_t*)ctx->nlseq.p, (const uint8_t*)ctx->streams.p, din,
