@@ -26,7 +26,8 @@ struct PinBuf { void* p = nullptr; size_t cap = 0; };
 
 struct xpngb_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, aux = nullptr, cur = nullptr;   // main stream, side stream for independent chains, stream of the next launch
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, pe0 = nullptr, pe1 = nullptr;
     int profile = 0;   // 1: per-kernel CUDA-event timing accumulated (serialises the launches); 2: also print to stderr
     struct ProfRow { const char* name; double ms; uint32_t count; };
@@ -58,17 +59,23 @@ struct xpngb_ctx {
     } while (0)
 #define LAUNCH(kernel, grid, block, smem, ...)                                                      \
     do {                                                                                            \
-        if (ctx->profile) cudaEventRecord(ctx->pe0, ctx->stream);                                   \
-        kernel<<<grid, block, smem, ctx->stream>>>(__VA_ARGS__);                                    \
+        if (ctx->profile) cudaEventRecord(ctx->pe0, ctx->cur);                                      \
+        kernel<<<grid, block, smem, ctx->cur>>>(__VA_ARGS__);                                       \
         ctx->launches++;                                                                            \
         CK(cudaGetLastError());                                                                     \
         if (ctx->profile) {                                                                         \
-            float ms_ = 0; cudaEventRecord(ctx->pe1, ctx->stream); cudaEventSynchronize(ctx->pe1);  \
+            float ms_ = 0; cudaEventRecord(ctx->pe1, ctx->cur); cudaEventSynchronize(ctx->pe1);     \
             cudaEventElapsedTime(&ms_, ctx->pe0, ctx->pe1);                                         \
             prof_add(ctx, #kernel, ms_);                                                            \
             if (ctx->profile > 1) fprintf(stderr, "[xpngb] %-28s %9.3f ms\n", #kernel, ms_);       \
         }                                                                                           \
     } while (0)
+
+// Independent serial chains (e.g. the value-stream blocks of level 2 while the context streams are walked)
+// run on the side stream: FORK makes it wait for everything launched so far, JOIN makes the main stream wait for it.
+#define FORK_AUX() do { CK(cudaEventRecord(ctx->ev_fork, ctx->stream)); CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0)); ctx->cur = ctx->aux; } while (0)
+#define BACK_TO_MAIN() do { ctx->cur = ctx->stream; } while (0)
+#define JOIN_AUX() do { ctx->cur = ctx->stream; CK(cudaEventRecord(ctx->ev_join, ctx->aux)); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); } while (0)
 
 static void prof_add(xpngb_ctx* ctx, const char* name, float ms) {
     for (auto& r : ctx->prof) if (!strcmp(r.name, name)) { r.ms += ms; r.count++; return; }
@@ -202,11 +209,14 @@ static int m2_encode_tiles(xpngb_ctx* ctx, const Plan& P, uint32_t ntiles, uint3
                    (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->blocks.p, (uint32_t*)ctx->tabs.p, ntiles, 0, 17, 0, 0 };
     if (17 * ntiles <= ctx->lat_max_blocks) {
         auto p_small = k_rans_v1_pair<16>; auto p_big = k_rans_v1_pair<256>;
+        FORK_AUX();                                   // alphabets above 16 symbols and the grey candidates: side stream
+        RansV1Args rb = ra; rb.c0 = 9; rb.nc = 8; rb.nmin = 16;
+        LAUNCH(p_big, (8 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 256 * PAIR_BLK * 16, rb);
+        rb.c0 = 0; rb.nc = 4; rb.nmin = 0; rb.grey = 1;
+        LAUNCH(p_big, (4 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 256 * PAIR_BLK * 16, rb);
+        BACK_TO_MAIN();
         LAUNCH(p_small, (17 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 16 * PAIR_BLK * 16, ra);
-        ra.c0 = 9; ra.nc = 8; ra.nmin = 16;
-        LAUNCH(p_big, (8 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 256 * PAIR_BLK * 16, ra);
-        ra.c0 = 0; ra.nc = 4; ra.nmin = 0; ra.grey = 1;
-        LAUNCH(p_big, (4 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 256 * PAIR_BLK * 16, ra);
+        JOIN_AUX();
     } else {
     auto k_small = k_rans_v1<16, 128>; auto k_big = k_rans_v1<256, 32>;
     LAUNCH(k_small, (17 * ntiles + 127) / 128, 128, 16 * 128 * 16, ra);
@@ -236,7 +246,11 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     xpngb_ctx* ctx = new xpngb_ctx();
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) { delete ctx; return 1; }
+    ctx->cur = ctx->stream;
     cudaEventCreate(&ctx->pe0); cudaEventCreate(&ctx->pe1);
     if (const char* e = getenv("XPNGB_PROFILE")) ctx->profile = atoi(e) ? 2 : 0;
     if (const char* e = getenv("XPNGB_CHUNK_MPIX")) { const long v = atol(e); if (v > 0) ctx->max_chunk_px = (uint64_t)v << 20; }
@@ -254,7 +268,7 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
 extern "C" void xpngb_destroy(xpngb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->aux);
     DevBuf* all[] = { &ctx->pixels, &ctx->norm, &ctx->files, &ctx->arena, &ctx->tiles, &ctx->imgs, &ctx->seg_tile, &ctx->costs,
                       &ctx->hist, &ctx->seginfo, &ctx->place, &ctx->vplace, &ctx->vcnt, &ctx->sym_area, &ctx->bits_area, &ctx->alpha,
                       &ctx->streams, &ctx->blocks, &ctx->state, &ctx->outs, &ctx->flags, &ctx->skip, &ctx->dimgs, &ctx->dtiles,
@@ -264,6 +278,8 @@ extern "C" void xpngb_destroy(xpngb_ctx* ctx) {
     if (ctx->pin_a.p) cudaFreeHost(ctx->pin_a.p);
     if (ctx->pin_b.p) cudaFreeHost(ctx->pin_b.p);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->pe0); cudaEventDestroy(ctx->pe1);
+    cudaStreamDestroy(ctx->aux);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -449,7 +465,7 @@ extern "C" int xpngb_encode(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32
                             int pixels_on_device, void* out, uint64_t out_cap, int out_on_device, uint64_t* out_offsets,
                             uint64_t* out_sizes) {
     if (!ctx) return 1;
-    ctx->err[0] = 0; ctx->launches = 0; ctx->last_ms = 0.f;
+    ctx->err[0] = 0; ctx->launches = 0; ctx->last_ms = 0.f; ctx->cur = ctx->stream;
     if (!imgs || !pixels || !out || !out_offsets || !out_sizes) FAIL("null argument");
     if (!(level == 1 || level == 2 || level == 7)) FAIL("level must be 1, 2 or 7");          // libxpng.c:729
     if (n == 0) return 0;
@@ -521,7 +537,7 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
                             const uint64_t* file_offsets, const uint64_t* file_sizes, void* pixels, uint64_t pixels_cap,
                             int pixels_on_device) {
     if (!ctx) return 1;
-    ctx->err[0] = 0; ctx->launches = 0; ctx->last_ms = 0.f;
+    ctx->err[0] = 0; ctx->launches = 0; ctx->last_ms = 0.f; ctx->cur = ctx->stream;
     if (!imgs || !files || !file_offsets || !file_sizes || !pixels) FAIL("null argument");
     if (n == 0) return 0;
     CK(cudaSetDevice(ctx->device));
@@ -589,6 +605,7 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     const uint32_t nseg = (uint32_t)P.seg_tile.size();
     const uint32_t* d_seg_tile = (const uint32_t*)ctx->seg_tile.p;
+    bool aux_busy = false;
     if (any1 || any2) {
         ENSURE(streams, P.str_total); ENSURE(nlseq, P.px_total); ENSURE(rows, P.row_total * sizeof(RowInfo));
         ENSURE(rowcnt, P.row_total * 4); ENSURE(edge, P.row_total * 16);
@@ -613,8 +630,12 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
     if (any2) {
         LAUNCH(k_dec_parse_m2, (ntiles + 127) / 128, 128, 0, d_tiles, d_imgs, din, d_dt, ntiles, d_err);
         if (17 * ntiles <= ctx->lat_max_blocks) {
-            RansV1LatArgs la{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 17, LAT_LUT_V1 };
-            LAUNCH(k_dec_rans_v1_lat, 17 * ntiles, 32, LAT_SMEM_V1, la);
+            RansV1LatArgs la{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 8, LAT_LUT_V1 };
+            FORK_AUX();                               // value streams: side stream, joined before the residual kernels
+            LAUNCH(k_dec_rans_v1_lat, 8 * ntiles, 32, LAT_SMEM_V1, la);
+            BACK_TO_MAIN(); aux_busy = true;
+            la.j0 = 8; la.nj = 9;                     // context streams (and grey planes), then the walk
+            LAUNCH(k_dec_rans_v1_lat, 9 * ntiles, 32, LAT_SMEM_V1, la);
         } else {
         RansV1DecArgs rv{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 9, 0, 16 };
         auto k8 = k_dec_rans_v1_small<8, 128>; auto k15 = k_dec_rans_v1_small<15, 128>; auto kbig = k_dec_rans_v1_big<32>;
@@ -642,6 +663,7 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
                       (uint32_t*)ctx->ccnt.p, (uint32_t*)ctx->cbit.p, (uint32_t*)ctx->resv.p, ntiles, d_err };
         LAUNCH(k_dec_chunk_hist, nseg, 256, 0, ch);
         LAUNCH(k_dec_chunk_scan, (ntiles + 3) / 4, 128, 0, ch);
+        if (aux_busy) JOIN_AUX();
         if (any1) LAUNCH(k_dec_residuals<1>, nseg, 256, 0, ch);
         if (any2) { LAUNCH(k_dec_residuals<2>, nseg, 256, 0, ch); LAUNCH(k_dec_residuals_grey, nseg, 256, 0, ch); }
         UnpredArgs ua{ d_tiles, d_imgs, d_dt, din, (const uint32_t*)ctx->resv.p, (const uint8_t*)ctx->plane.p, (const RowInfo*)ctx->rows.p,

@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(32) k_dec_rans_v2_lat(RansDecArgs A, uint32_t 
 // v1 blocks (level 2; libxpng.c:262-301).  Block order: long value streams first, so that the longest
 // chains start in the first wave of CTAs.
 // ---------------------------------------------------------------------------------------------------
-__device__ __constant__ const uint8_t LAT_M2_ORDER[17] = { 12, 13, 11, 14, 15, 16, 0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 9 };
+__device__ __constant__ const uint8_t LAT_M2_ORDER[17] = { 12, 13, 11, 14, 15, 16, 10, 9, 0, 1, 2, 3, 4, 5, 6, 7, 8 };   // values first (0..7), contexts (8..16)
 
 struct RansV1LatArgs {
     const TileDesc* tiles;

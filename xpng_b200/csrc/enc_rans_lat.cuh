@@ -47,11 +47,13 @@ __device__ __forceinline__ uint32_t pair_chain(const uint4* E, const int pb, con
         if (mine) { if (VER == 2) wbase[wcount + before] = pend_w; else *(wbase - 1 - (int64_t)(wcount + before)) = pend_w; }
         wcount += p0 + p1;
     };
+    uint4 vnext = make_uint4(0, 0, 0, 0);
+    if (G) vnext = in16[VER == 2 ? 0 : G - 1];
     for (uint32_t g = 0; g < Gmax; g++) {
         const bool gv = g < G;
         const uint32_t gi = gv ? (VER == 2 ? g : G - 1 - g) : 0u;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (gv) v = in16[gi];
+        const uint4 v = vnext;
+        if (g + 1 < G) vnext = in16[VER == 2 ? g + 1 : G - 2 - g];   // the next group's symbols arrive while this group is coded
         const uint32_t u[4] = { (h ? v.x >> 8 : v.x) & 0x00FF00FFu, (h ? v.y >> 8 : v.y) & 0x00FF00FFu, (h ? v.z >> 8 : v.z) & 0x00FF00FFu,
                                 (h ? v.w >> 8 : v.w) & 0x00FF00FFu };
 #pragma unroll
