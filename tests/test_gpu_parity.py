@@ -147,3 +147,61 @@ def test_ycocg_r_side_kernel(codec):
     assert ycc[:, 0].min() == 0 and ycc[:, 0].max() == 255
     assert ycc[:, 1].min() == -255 and ycc[:, 1].max() == 255 and ycc[:, 2].min() == -255 and ycc[:, 2].max() == 255
     assert np.array_equal(codec.ycocg_inverse(ycc), rgb)
+
+
+def test_throughput_kernel_family(monkeypatch):
+    """Large batches switch from the warp-per-block (latency) entropy kernels to the lane-per-block ones
+    (XPNGB_LAT_MAX_BLOCKS, read when the context is created): both families must produce the same bytes."""
+    import xpng_b200
+    monkeypatch.setenv("XPNGB_LAT_MAX_BLOCKS", "0")
+    cd = xpng_b200.Codec(0)
+    try:
+        imgs = [synth.rgb(500, 700, 81), synth.rgba(450, 460, 82), synth.gray_as_rgb(300, 520, 83), synth.noise(90, 70, 84),
+                np.full((50, 60, 3), 7, np.uint8)]
+        for lv in (1, 2):
+            want = [po.encode(lv, im) for im in imgs]
+            assert cd.encode(lv, imgs) == want
+            for b, im in zip(cd.decode(want), imgs):
+                assert np.array_equal(b, po.normalize(im))
+    finally:
+        cd.close()
+
+
+def test_largest_tile_uses_global_walk(codec):
+    """A 666 x 666 image is ONE tile (libxpng.c:57-80) of 443 556 pixels: its context streams do not fit the
+    shared-memory walk, so the register-window walk over global memory runs instead."""
+    px = synth.rgb(666, 666, 91)
+    for lv in (1, 2):
+        want = po.encode(lv, px)
+        assert codec.encode(lv, [px])[0] == want
+        assert np.array_equal(codec.decode([want])[0], px)
+
+
+def test_many_small_images_one_call(codec):
+    """More than 592 tiles in one call (4 tiles per CTA variants of the per-tile kernels)."""
+    imgs = [synth.rgb(20 + (i % 7), 24 + (i % 5), 2000 + i) for i in range(640)]
+    for lv in (1, 2):
+        want = [po.encode(lv, im) for im in imgs]
+        assert codec.encode(lv, imgs) == want
+        for b, im in zip(codec.decode(want), imgs):
+            assert np.array_equal(b, im)
+
+
+def test_fuzzed_files_never_crash(codec):
+    """Random byte corruption of valid files: the decoder may fail (RuntimeError) or return garbage, but it must
+    neither hang nor fault (a CUDA fault would poison the context and fail the final clean decode)."""
+    rng = np.random.default_rng(7)
+    px = synth.rgba(300, 340, 93)
+    rgbpx = synth.rgb(320, 300, 94)
+    for lv, img in ((1, px), (1, rgbpx), (2, rgbpx), (2, synth.gray_as_rgb(200, 260, 95))):
+        good = po.encode(lv, img)
+        for k in range(24):
+            f = bytearray(good)
+            for _ in range(int(rng.integers(1, 6))):
+                pos = int(rng.integers(8, len(f)))
+                f[pos] = int(rng.integers(0, 256))
+            try:
+                codec.decode([bytes(f)])
+            except RuntimeError:
+                pass
+        assert np.array_equal(codec.decode([good])[0], po.normalize(img))

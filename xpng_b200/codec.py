@@ -17,7 +17,8 @@ class LibraryMissing(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(HERE, "libxpng_b200.so")
+    # XPNGB_LIB: developer override for A/B builds of the same library (tools/abtest.sh)
+    return os.environ.get("XPNGB_LIB") or os.path.join(HERE, "libxpng_b200.so")
 
 
 class _Image(C.Structure):

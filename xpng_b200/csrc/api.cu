@@ -36,7 +36,7 @@ struct xpngb_ctx {
     float last_ms = 0.f;
     uint32_t launches = 0;
     uint64_t max_chunk_px = 1ull << 30;
-    uint32_t lat_max_blocks = 8192;   // entropy blocks per launch up to which the warp-per-block (latency) kernels are used
+    uint32_t lat_max_blocks = 32768;  // entropy blocks per launch up to which the warp-per-block (latency) kernels are used (measured crossover, profiles/)
     // device scratch
     DevBuf pixels, norm, files, arena, tiles, imgs, seg_tile, costs, hist, seginfo, place, vplace, vcnt, sym_area,
         bits_area, alpha, streams, blocks, state, outs, flags, skip, dimgs, dtiles, plane, nlseq, rowcnt, rowbits,
@@ -211,11 +211,11 @@ static int m2_encode_tiles(xpngb_ctx* ctx, const Plan& P, uint32_t ntiles, uint3
         auto p_small = k_rans_v1_pair<16>; auto p_big = k_rans_v1_pair<256>;
         FORK_AUX();                                   // alphabets above 16 symbols and the grey candidates: side stream
         RansV1Args rb = ra; rb.c0 = 9; rb.nc = 8; rb.nmin = 16;
-        LAUNCH(p_big, (8 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 256 * PAIR_BLK * 16, rb);
+        LAUNCH(p_big, (8 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 16, rb);
         rb.c0 = 0; rb.nc = 4; rb.nmin = 0; rb.grey = 1;
-        LAUNCH(p_big, (4 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 256 * PAIR_BLK * 16, rb);
+        LAUNCH(p_big, (4 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 16, rb);
         BACK_TO_MAIN();
-        LAUNCH(p_small, (17 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 16 * PAIR_BLK * 16, ra);
+        LAUNCH(p_small, (17 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 17 * PAIR_BLK * 16, ra);
         JOIN_AUX();
     } else {
     auto k_small = k_rans_v1<16, 128>; auto k_big = k_rans_v1<256, 32>;
@@ -257,8 +257,8 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     { auto k_big = k_rans_v2<256, 32>; cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 16); }
     m2_set_attributes();
     if (const char* e = getenv("XPNGB_LAT_MAX_BLOCKS")) ctx->lat_max_blocks = (uint32_t)atol(e);
-    { auto p = k_rans_v2_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * PAIR_BLK * 16); }
-    { auto p = k_rans_v1_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * PAIR_BLK * 16); }
+    { auto p = k_rans_v2_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * PAIR_BLK * 16); }
+    { auto p = k_rans_v1_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * PAIR_BLK * 16); }
     cudaFuncSetAttribute(k_dec_walk_smem<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WALK_SMEM_MAX_SYMS / 8 + 32) * 4);
     cudaFuncSetAttribute(k_dec_rans_v1_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, LAT_SMEM_V1);
     *out = ctx;
@@ -424,8 +424,8 @@ static int encode_chunk(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32_t n
                        (const uint8_t*)ctx->alpha.p, (uint8_t*)ctx->blocks.p, ntiles, 0, 9 };
         if (9 * ntiles <= ctx->lat_max_blocks) {
             auto p_small = k_rans_v2_pair<16>; auto p_big = k_rans_v2_pair<256>;
-            LAUNCH(p_small, (9 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 16 * PAIR_BLK * 16, ra);
-            if (P.any_rgba) { ra.c0 = 9; ra.nc = 1; LAUNCH(p_big, (ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 256 * PAIR_BLK * 16, ra); }
+            LAUNCH(p_small, (9 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 17 * PAIR_BLK * 16, ra);
+            if (P.any_rgba) { ra.c0 = 9; ra.nc = 1; LAUNCH(p_big, (ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 16, ra); }
         } else {
         auto k_small = k_rans_v2<9, 128>; auto k_big = k_rans_v2<256, 32>;
         LAUNCH(k_small, (9 * ntiles + 127) / 128, 128, 9 * 128 * 16, ra);

@@ -20,11 +20,13 @@ namespace xpb {
 constexpr int PAIR_BLK = 16;   // blocks per warp
 
 // One warp: the 2-lane recurrences of up to 16 blocks.  `live`: this lane's block runs the recurrence.
-// E = &etab[blk] with layout [sym][PAIR_BLK].  Emission e (0-based) goes to wbase[e] (VER 2) or
+// E = &etab[blk] with layout [sym][PAIR_BLK]; row `ident` holds the identity symbol (rcp = 0, bias = 0,
+// freq field 0xFFFF: never renormalises, x' = x), which steps outside the lane's stream use so that the
+// recurrence needs no validity select.  Emission e (0-based) goes to wbase[e] (VER 2) or
 // wbase[-1 - e] (VER 1).  Returns the block's word count; xlo/xhi hold the lane's final state.
 template <int VER>
-__device__ __forceinline__ uint32_t pair_chain(const uint4* E, const int pb, const uint8_t* in, const uint32_t n, const bool live, uint32_t* wbase,
-                                               uint32_t& xlo, uint32_t& xhi) {
+__device__ __forceinline__ uint32_t pair_chain(const uint4* E, const uint32_t ident, const int pb, const uint8_t* in, const uint32_t n, const bool live,
+                                               uint32_t* wbase, uint32_t& xlo, uint32_t& xhi) {
     const uint32_t lane = threadIdx.x & 31, h = lane & 1, bsh = lane & 30u;
     xlo = 0x80000000u; xhi = 0;                                   // RANS64_L = 2^31
     auto core = [&](const uint4 e) {                              // state update after the renormalisation decision
@@ -41,7 +43,7 @@ __device__ __forceinline__ uint32_t pair_chain(const uint4* E, const int pb, con
     for (int o = 16; o; o >>= 1) Gmax = max(Gmax, __shfl_xor_sync(0xffffffffu, Gmax, o));
     const uint4* in16 = reinterpret_cast<const uint4*>(in);
     uint32_t wcount = 0, pend_w = 0, pend_bal = 0;
-    auto flush = [&]() {                                          // store of the previous step
+    auto flush = [&]() {                                          // store of the previous step (its ballot is one step old)
         const uint32_t bits = pend_bal >> bsh, p0 = bits & 1u, p1 = (bits >> 1) & 1u;
         const uint32_t mine = h ? p1 : p0, before = VER == 2 ? (h ? p0 : 0u) : (h ? 0u : p1);
         if (mine) { if (VER == 2) wbase[wcount + before] = pend_w; else *(wbase - 1 - (int64_t)(wcount + before)) = pend_w; }
@@ -60,16 +62,15 @@ __device__ __forceinline__ uint32_t pair_chain(const uint4* E, const int pb, con
         for (int jj = 0; jj < 8; jj++) {
             const int j = VER == 2 ? jj : 7 - jj;
             const bool valid = gv && (16u * gi + 2u * j + h) < nn;
-            const uint32_t s = valid ? (u[j >> 1] >> (16 * (j & 1))) & 0xFFu : 0u;   // bytes past the stream end are scratch
+            const uint32_t s = valid ? (u[j >> 1] >> (16 * (j & 1))) & 0xFFu : ident;   // bytes past the stream end are scratch
             const uint4 e = E[s * PAIR_BLK];
             flush();
-            const bool p = valid && xhi >= ((e.w & 0xFFFFu) << (31 - pb));   // x >= freq << (63 - pb)  (libxpng.c:370)
+            const bool p = xhi >= ((e.w & 0xFFFFu) << (31 - pb));            // x >= freq << (63 - pb)  (libxpng.c:370)
             pend_w = xlo;
             pend_bal = __ballot_sync(0xffffffffu, p);
             const uint32_t olo = p ? xhi : xlo, ohi = p ? 0u : xhi;
             xlo = olo; xhi = ohi;
             core(e);
-            xlo = valid ? xlo : olo; xhi = valid ? xhi : ohi;
         }
     }
     flush();
@@ -81,8 +82,9 @@ __device__ __forceinline__ uint32_t pair_chain(const uint4* E, const int pb, con
 // ---------------------------------------------------------------------------------------------------
 template <int NSYM>
 __global__ void __launch_bounds__(32) k_rans_v2_pair(RansV2Args A) {
-    extern __shared__ __align__(16) uint4 etab[];   // [NSYM][PAIR_BLK]
+    extern __shared__ __align__(16) uint4 etab[];   // [NSYM + 1][PAIR_BLK], last row = identity
     const uint32_t lane = threadIdx.x, h = lane & 1, blk = lane >> 1;
+    if (h == 0) etab[NSYM * PAIR_BLK + blk] = make_uint4(0u, 0u, 0u, 0xFFFFu);
     const uint32_t id = blockIdx.x * PAIR_BLK + blk;
     const bool exists = id < A.nc * A.ntiles;
     const uint32_t c = A.c0 + (exists ? id / A.ntiles : 0), tile = exists ? id % A.ntiles : 0;
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(32) k_rans_v2_pair(RansV2Args A) {
     live = __shfl_sync(0xffffffffu, (int)live, lane & 30u) != 0;
     __syncwarp();
     uint32_t xlo, xhi;
-    const uint32_t words = pair_chain<2>(etab + blk, pb, in, n, live, o + 3, xlo, xhi);
+    const uint32_t words = pair_chain<2>(etab + blk, NSYM, pb, in, n, live, o + 3, xlo, xhi);
     const uint32_t x1lo = __shfl_sync(0xffffffffu, xlo, lane | 1u), x1hi = __shfl_sync(0xffffffffu, xhi, lane | 1u);
     if (!live || h) return;
     uint32_t* wp = o + 3 + words;
@@ -151,8 +153,9 @@ __global__ void __launch_bounds__(32) k_rans_v2_pair(RansV2Args A) {
 // ---------------------------------------------------------------------------------------------------
 template <int NSYM>
 __global__ void __launch_bounds__(32) k_rans_v1_pair(RansV1Args A) {
-    extern __shared__ __align__(16) uint4 etab[];   // [NSYM][PAIR_BLK]
+    extern __shared__ __align__(16) uint4 etab[];   // [NSYM + 1][PAIR_BLK], last row = identity
     const uint32_t lane = threadIdx.x, h = lane & 1, blk = lane >> 1;
+    if (h == 0) etab[NSYM * PAIR_BLK + blk] = make_uint4(0u, 0u, 0u, 0xFFFFu);
     const uint32_t id = blockIdx.x * PAIR_BLK + blk;
     bool exists = id < A.nc * A.ntiles;
     const uint32_t c = A.c0 + (exists ? id / A.ntiles : 0), tile = exists ? id % A.ntiles : 0;
@@ -205,7 +208,7 @@ __global__ void __launch_bounds__(32) k_rans_v1_pair(RansV1Args A) {
     live = __shfl_sync(0xffffffffu, (int)live, lane & 30u) != 0;
     __syncwarp();
     uint32_t xlo, xhi;
-    const uint32_t words = pair_chain<1>(etab + blk, pb, in, n, live, rend, xlo, xhi);        // :215-245, words go down from the region end
+    const uint32_t words = pair_chain<1>(etab + blk, NSYM, pb, in, n, live, rend, xlo, xhi);        // :215-245, words go down from the region end
     const uint32_t x1lo = __shfl_sync(0xffffffffu, xlo, lane | 1u), x1hi = __shfl_sync(0xffffffffu, xhi, lane | 1u);
     if (!live || h) return;
     uint32_t* wp = rend - words;
