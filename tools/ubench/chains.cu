@@ -86,6 +86,91 @@ __global__ void k_dec_d2(const uint32_t* lut_g, const uint32_t* words, uint32_t 
     if (lane == 0) { cyc[0] = t1 - t0; out[n] = (uint8_t)(alo + blo + ahi + bhi); }
 }
 
+
+__global__ void k_dec_d2one(const uint32_t* lut_g, const uint32_t* words, uint32_t nwords, uint32_t n, int pb, uint8_t* out, long long* cyc) {
+    extern __shared__ uint32_t sm[];
+    uint32_t* lut = sm; uint32_t* ring = sm + (1u << pb);
+    const uint32_t lane = threadIdx.x;
+    for (uint32_t i = lane; i < (1u << pb); i += 32) lut[i] = lut_g[i];
+    for (uint32_t i = lane; i < RING + 8; i += 32) ring[i] = words[(i % RING) % nwords];
+    __syncwarp();
+    const uint32_t mask = (1u << pb) - 1u;
+    uint32_t alo = 0x12345678u, ahi = 0x1u, blo = 0x9abcdef0u, bhi = 0x2u, kb = 0;   // kb: byte offset into the ring
+    uint32_t mk[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) mk[j] = lane == (uint32_t)j ? 0xFFFFFFFFu : 0u;
+    const char* ringb = reinterpret_cast<const char*>(ring);
+    long long t0 = clock64();
+    for (uint32_t i = 0; i + 32 <= n; i += 32) {
+        uint32_t keep = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            const uint32_t c0 = *reinterpret_cast<const uint32_t*>(ringb + kb), c1 = *reinterpret_cast<const uint32_t*>(ringb + kb + 4);
+            uint32_t ea, eb;
+            { const uint32_t slot = alo & mask; ea = lut[slot];
+              const uint32_t qlo = __funnelshift_r(alo, ahi, pb), qhi = ahi >> pb, f = ea >> 18, b = ea & 0x3FFFu;
+              const unsigned long long t = (unsigned long long)f * qlo + b; alo = (uint32_t)t; ahi = f * qhi + (uint32_t)(t >> 32); }
+            eb = 0;
+            const bool pa = (ahi | (alo & 0x80000000u)) == 0, pbb = false;
+            const uint32_t wb = pa ? c1 : c0;
+            ahi = pa ? alo : ahi; alo = pa ? c0 : alo;
+            bhi = pbb ? blo : bhi; blo = pbb ? wb : blo;
+            kb = (kb + (pa ? 4u : 0u) + (pbb ? 4u : 0u)) & (RING * 4 - 1);
+            keep |= (ea & mk[j]) | (eb & mk[j + 1]);
+        }
+        out[i + lane] = (uint8_t)((keep >> 14) & 15u);
+    }
+    long long t1 = clock64();
+    if (lane == 0) { cyc[0] = t1 - t0; out[n] = (uint8_t)(alo + blo + ahi + bhi); }
+}
+
+
+// D3: the renormalisation predicate comes from a second table: x' = f*q + b < 2^31  <=>  qhi == 0 && qlo <= T[slot],
+// T[slot] = floor((2^31 - 1 - b) / f): the predicate no longer waits for the 64-bit multiply, and the next slot only
+// needs the LOW word of x' (a 32-bit IMAD).
+__global__ void k_dec_d3(const uint32_t* lut_g, const uint32_t* lutT_g, const uint32_t* words, uint32_t nwords, uint32_t n, int pb, uint8_t* out, long long* cyc) {
+    extern __shared__ uint32_t sm[];
+    uint32_t* lut = sm; uint32_t* lutT = sm + (1u << pb); uint32_t* ring = sm + (2u << pb);
+    const uint32_t lane = threadIdx.x;
+    for (uint32_t i = lane; i < (1u << pb); i += 32) { lut[i] = lut_g[i]; lutT[i] = lutT_g[i]; }
+    for (uint32_t i = lane; i < RING + 8; i += 32) ring[i] = words[(i % RING) % nwords];
+    __syncwarp();
+    const uint32_t mask = (1u << pb) - 1u;
+    uint32_t alo = 0x12345678u, ahi = 0x1u, blo = 0x9abcdef0u, bhi = 0x2u, kb = 0;
+    uint32_t mk[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) { mk[j] = lane == (uint32_t)j ? 0xFFFFFFFFu : 0u; asm volatile("" : "+r"(mk[j])); }
+    const char* ringb = reinterpret_cast<const char*>(ring);
+    long long t0 = clock64();
+    for (uint32_t i = 0; i + 32 <= n; i += 32) {
+        uint32_t keep = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            const uint32_t c0 = *reinterpret_cast<const uint32_t*>(ringb + kb), c1 = *reinterpret_cast<const uint32_t*>(ringb + kb + 4);
+            uint32_t ea, eb; bool pa, pq;
+            uint32_t alo2, ahi2, blo2, bhi2;
+            { const uint32_t slot = alo & mask; ea = lut[slot]; const uint32_t T = lutT[slot];
+              const uint32_t qlo = __funnelshift_r(alo, ahi, pb), qhi = ahi >> pb, f = ea >> 18, b = ea & 0x3FFFu;
+              pa = (qhi == 0) & (qlo <= T);
+              alo2 = f * qlo + b;                                             // low word: 32-bit IMAD
+              ahi2 = __umulhi(f, qlo) + f * qhi + (alo2 < b ? 1u : 0u); }     // high word, off the slot path
+            { const uint32_t slot = blo & mask; eb = lut[slot]; const uint32_t T = lutT[slot];
+              const uint32_t qlo = __funnelshift_r(blo, bhi, pb), qhi = bhi >> pb, f = eb >> 18, b = eb & 0x3FFFu;
+              pq = (qhi == 0) & (qlo <= T);
+              blo2 = f * qlo + b;
+              bhi2 = __umulhi(f, qlo) + f * qhi + (blo2 < b ? 1u : 0u); }
+            const uint32_t wb = pa ? c1 : c0;
+            ahi = pa ? alo2 : ahi2; alo = pa ? c0 : alo2;
+            bhi = pq ? blo2 : bhi2; blo = pq ? wb : blo2;
+            kb = (kb + (pa ? 4u : 0u) + (pq ? 4u : 0u)) & (RING * 4 - 1);
+            keep |= (ea & mk[j]) | (eb & mk[j + 1]);
+        }
+        out[i + lane] = (uint8_t)((keep >> 14) & 15u);
+    }
+    long long t1 = clock64();
+    if (lane == 0) { cyc[0] = t1 - t0; out[n] = (uint8_t)(alo + blo + ahi + bhi); }
+}
+
 // issue-rate probes: independent instructions in one warp
 __global__ void k_issue(uint32_t* out, long long* cyc, uint32_t a) {
     uint32_t v[8]; for (int i = 0; i < 8; i++) v[i] = threadIdx.x + i;
@@ -830,6 +915,17 @@ int main() {
     printf("dec_d1 1 lane        %7.2f cycles/symbol\n", (double)cyc[0] / n);
     for (int r = 0; r < 2; r++) { k_dec_d2<<<1, 32, sm + 64>>>(d_lut, d_words, 4096, n, pb, d_out, cyc); cudaDeviceSynchronize(); }
     printf("dec_d2               %7.2f cycles/symbol\n", (double)cyc[0] / n);
+    {   std::vector<uint32_t> lutT(1 << pb);
+        for (int s2 = 0; s2 < 9; s2++) for (uint32_t i = cum[s2]; i < cum[s2 + 1]; i++) lutT[i] = (uint32_t)((0x7FFFFFFFull - (i - cum[s2])) / (cum[s2 + 1] - cum[s2]));
+        uint32_t* d_lutT; cudaMalloc(&d_lutT, lutT.size() * 4); cudaMemcpy(d_lutT, lutT.data(), lutT.size() * 4, cudaMemcpyHostToDevice);
+        std::vector<uint8_t> o2(n), o3(n);
+        k_dec_d2<<<1, 32, sm + 64>>>(d_lut, d_words, 4096, n, pb, d_out, cyc); cudaDeviceSynchronize(); cudaMemcpy(o2.data(), d_out, n, cudaMemcpyDeviceToHost);
+        for (int r = 0; r < 2; r++) { k_dec_d2one<<<1, 32, sm + 64>>>(d_lut, d_words, 4096, n, pb, d_out, cyc); cudaDeviceSynchronize(); }
+        printf("dec_d2 one state     %7.2f cycles/step\n", (double)cyc[0] / (n / 2));
+        cudaFuncSetAttribute(k_dec_d3, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * sm + 64);
+        for (int r = 0; r < 2; r++) { k_dec_d3<<<1, 32, 2 * sm + 64>>>(d_lut, d_lutT, d_words, 4096, n, pb, d_out, cyc); cudaDeviceSynchronize(); }
+        cudaMemcpy(o3.data(), d_out, n, cudaMemcpyDeviceToHost);
+        printf("dec_d3 (pred table)  %7.2f cycles/symbol %s\n", (double)cyc[0] / n, o2 == o3 ? "same symbols as d2" : "MISMATCH vs d2"); }
     for (int r = 0; r < 2; r++) { k_issue<<<1, 32>>>((uint32_t*)d_out, cyc, 5); cudaDeviceSynchronize(); }
     printf("issue 8 indep (xor,add)   %7.2f cycles per 16 ops (SASS-count dependent)\n", (double)cyc[0] / 4096);
     for (int r = 0; r < 2; r++) { k_issue_mix<<<1, 32>>>((uint32_t*)d_out, cyc, 5); cudaDeviceSynchronize(); }

@@ -26,8 +26,8 @@ struct PinBuf { void* p = nullptr; size_t cap = 0; };
 
 struct xpngb_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr, aux = nullptr, cur = nullptr;   // main stream, side stream for independent chains, stream of the next launch
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t stream = nullptr, side[2] = { nullptr, nullptr }, cur = nullptr;   // main stream, two side streams for independent chains, stream of the next launch
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = { nullptr, nullptr };
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, pe0 = nullptr, pe1 = nullptr;
     int profile = 0;   // 1: per-kernel CUDA-event timing accumulated (serialises the launches); 2: also print to stderr
     struct ProfRow { const char* name; double ms; uint32_t count; };
@@ -73,9 +73,9 @@ struct xpngb_ctx {
 
 // Independent serial chains (e.g. the value-stream blocks of level 2 while the context streams are walked)
 // run on the side stream: FORK makes it wait for everything launched so far, JOIN makes the main stream wait for it.
-#define FORK_AUX() do { CK(cudaEventRecord(ctx->ev_fork, ctx->stream)); CK(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0)); ctx->cur = ctx->aux; } while (0)
+#define FORK_SIDE(k) do { CK(cudaEventRecord(ctx->ev_fork, ctx->stream)); CK(cudaStreamWaitEvent(ctx->side[k], ctx->ev_fork, 0)); ctx->cur = ctx->side[k]; } while (0)
 #define BACK_TO_MAIN() do { ctx->cur = ctx->stream; } while (0)
-#define JOIN_AUX() do { ctx->cur = ctx->stream; CK(cudaEventRecord(ctx->ev_join, ctx->aux)); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0)); } while (0)
+#define JOIN_SIDE(k) do { ctx->cur = ctx->stream; CK(cudaEventRecord(ctx->ev_join[k], ctx->side[k])); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0)); } while (0)
 
 static void prof_add(xpngb_ctx* ctx, const char* name, float ms) {
     for (auto& r : ctx->prof) if (!strcmp(r.name, name)) { r.ms += ms; r.count++; return; }
@@ -176,8 +176,10 @@ static int upload_plan(xpngb_ctx* ctx, const Plan& P) {
 // ------------------------------------------------------------------------------------------------
 // Level 2 host side
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t LAT_LUT_V2 = 1024 + 32768, LAT_SMEM_V2 = LAT_CUM_WORDS * 4 + LAT_LUT_V2 + LAT_RING_WORDS * 4;   // 2^12 x 4 B direct table or byte table 2^15 + 1 KiB
-constexpr uint32_t LAT_LUT_V1 = 65536, LAT_SMEM_V1 = LAT_CUM_WORDS * 4 + LAT_LUT_V1 + LAT_RING_WORDS * 4;          // 2^14 x 4 B direct table
+// Shared memory per entropy-block CTA = cum[] + tables + word ring.  Tables are sized per launch so that every
+// chain of a frame is resident at once (one level: 4 B x 2^PROB_BITS; two levels: 1 KiB + 2^PROB_BITS bytes).
+constexpr uint32_t lat_smem(uint32_t lut_bytes) { return LAT_CUM_WORDS * 4 + lut_bytes + LAT_RING_WORDS * 4; }
+constexpr uint32_t LUT_ONE_12 = 4u << 12, LUT_ONE_14 = 4u << 14, LUT_TWO_14 = 1024 + (1u << 14), LUT_TWO_15 = 1024 + (1u << 15);
 
 static void m2_set_attributes() {
     auto k_big = k_rans_v1<256, 32>;
@@ -209,14 +211,14 @@ static int m2_encode_tiles(xpngb_ctx* ctx, const Plan& P, uint32_t ntiles, uint3
                    (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->blocks.p, (uint32_t*)ctx->tabs.p, ntiles, 0, 17, 0, 0 };
     if (17 * ntiles <= ctx->lat_max_blocks) {
         auto p_small = k_rans_v1_pair<16>; auto p_big = k_rans_v1_pair<256>;
-        FORK_AUX();                                   // alphabets above 16 symbols and the grey candidates: side stream
+        FORK_SIDE(0);                                 // alphabets above 16 symbols and the grey candidates: side stream
         RansV1Args rb = ra; rb.c0 = 9; rb.nc = 8; rb.nmin = 16;
-        LAUNCH(p_big, (8 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 16, rb);
+        LAUNCH(p_big, (8 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, rb);
         rb.c0 = 0; rb.nc = 4; rb.nmin = 0; rb.grey = 1;
-        LAUNCH(p_big, (4 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 16, rb);
+        LAUNCH(p_big, (4 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, rb);
         BACK_TO_MAIN();
-        LAUNCH(p_small, (17 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 17 * PAIR_BLK * 16, ra);
-        JOIN_AUX();
+        LAUNCH(p_small, (17 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 17 * PAIR_BLK * 24, ra);
+        JOIN_SIDE(0);
     } else {
     auto k_small = k_rans_v1<16, 128>; auto k_big = k_rans_v1<256, 32>;
     LAUNCH(k_small, (17 * ntiles + 127) / 128, 128, 16 * 128 * 16, ra);
@@ -246,9 +248,11 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     xpngb_ctx* ctx = new xpngb_ctx();
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->side[0], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->side[1], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) { delete ctx; return 1; }
     ctx->cur = ctx->stream;
     cudaEventCreate(&ctx->pe0); cudaEventCreate(&ctx->pe1);
@@ -257,10 +261,10 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     { auto k_big = k_rans_v2<256, 32>; cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 16); }
     m2_set_attributes();
     if (const char* e = getenv("XPNGB_LAT_MAX_BLOCKS")) ctx->lat_max_blocks = (uint32_t)atol(e);
-    { auto p = k_rans_v2_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * PAIR_BLK * 16); }
-    { auto p = k_rans_v1_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * PAIR_BLK * 16); }
+    { auto p = k_rans_v2_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * PAIR_BLK * 24); }
+    { auto p = k_rans_v1_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * PAIR_BLK * 24); }
     cudaFuncSetAttribute(k_dec_walk_smem<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WALK_SMEM_MAX_SYMS / 8 + 32) * 4);
-    cudaFuncSetAttribute(k_dec_rans_v1_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, LAT_SMEM_V1);
+    cudaFuncSetAttribute(k_dec_rans_v1_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, lat_smem(LUT_ONE_14));
     *out = ctx;
     return 0;
 }
@@ -268,7 +272,7 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
 extern "C" void xpngb_destroy(xpngb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->aux);
+    cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->side[0]); cudaStreamSynchronize(ctx->side[1]);
     DevBuf* all[] = { &ctx->pixels, &ctx->norm, &ctx->files, &ctx->arena, &ctx->tiles, &ctx->imgs, &ctx->seg_tile, &ctx->costs,
                       &ctx->hist, &ctx->seginfo, &ctx->place, &ctx->vplace, &ctx->vcnt, &ctx->sym_area, &ctx->bits_area, &ctx->alpha,
                       &ctx->streams, &ctx->blocks, &ctx->state, &ctx->outs, &ctx->flags, &ctx->skip, &ctx->dimgs, &ctx->dtiles,
@@ -278,8 +282,8 @@ extern "C" void xpngb_destroy(xpngb_ctx* ctx) {
     if (ctx->pin_a.p) cudaFreeHost(ctx->pin_a.p);
     if (ctx->pin_b.p) cudaFreeHost(ctx->pin_b.p);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
-    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->pe0); cudaEventDestroy(ctx->pe1);
-    cudaStreamDestroy(ctx->aux);
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join[0]); cudaEventDestroy(ctx->ev_join[1]); cudaEventDestroy(ctx->pe0); cudaEventDestroy(ctx->pe1);
+    cudaStreamDestroy(ctx->side[0]); cudaStreamDestroy(ctx->side[1]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -424,8 +428,8 @@ static int encode_chunk(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32_t n
                        (const uint8_t*)ctx->alpha.p, (uint8_t*)ctx->blocks.p, ntiles, 0, 9 };
         if (9 * ntiles <= ctx->lat_max_blocks) {
             auto p_small = k_rans_v2_pair<16>; auto p_big = k_rans_v2_pair<256>;
-            LAUNCH(p_small, (9 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 17 * PAIR_BLK * 16, ra);
-            if (P.any_rgba) { ra.c0 = 9; ra.nc = 1; LAUNCH(p_big, (ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 16, ra); }
+            LAUNCH(p_small, (9 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 17 * PAIR_BLK * 24, ra);
+            if (P.any_rgba) { ra.c0 = 9; ra.nc = 1; LAUNCH(p_big, (ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, ra); }
         } else {
         auto k_small = k_rans_v2<9, 128>; auto k_big = k_rans_v2<256, 32>;
         LAUNCH(k_small, (9 * ntiles + 127) / 128, 128, 9 * 128 * 16, ra);
@@ -605,7 +609,7 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     const uint32_t nseg = (uint32_t)P.seg_tile.size();
     const uint32_t* d_seg_tile = (const uint32_t*)ctx->seg_tile.p;
-    bool aux_busy = false;
+    bool side_busy[2] = { false, false };
     if (any1 || any2) {
         ENSURE(streams, P.str_total); ENSURE(nlseq, P.px_total); ENSURE(rows, P.row_total * sizeof(RowInfo));
         ENSURE(rowcnt, P.row_total * 4); ENSURE(edge, P.row_total * 16);
@@ -617,25 +621,35 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
         LAUNCH(k_dec_parse_m1, (ntiles + 127) / 128, 128, 0, d_tiles, d_imgs, din, d_dt, ntiles, d_err);
         RansDecArgs ra{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, (uint8_t*)ctx->alpha.p, ntiles, 0, 9 };
         const bool lat = 9 * ntiles <= ctx->lat_max_blocks;
-        if (lat) LAUNCH(k_dec_rans_v2_lat, 9 * ntiles, 32, LAT_SMEM_V2, ra, LAT_LUT_V2);
-        else LAUNCH(k_dec_rans_v2_small<128>, (9 * ntiles + 127) / 128, 128, 0, ra);
-        if (P.any_rgba) {
-            if (lat) { ra.c0 = 9; ra.nc = 1; LAUNCH(k_dec_rans_v2_lat, ntiles, 32, LAT_SMEM_V2, ra, LAT_LUT_V2); }
-            else LAUNCH(k_dec_rans_v2_big<32>, (ntiles + 31) / 32, 32, 32 * 258 * 2 + 32 * 260, ra);
+        if (P.any_rgba) {                             // the alpha plane is independent of the context walk: side stream
+            FORK_SIDE(1); side_busy[1] = true;
+            RansDecArgs rb = ra; rb.c0 = 9; rb.nc = 1;
+            if (lat) LAUNCH(k_dec_rans_v2_lat, ntiles, 32, lat_smem(LUT_TWO_15), rb, LUT_TWO_15);
+            else LAUNCH(k_dec_rans_v2_big<32>, (ntiles + 31) / 32, 32, 32 * 258 * 2 + 32 * 260, rb);
             AlphaArgs al{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->alpha.p, (uint8_t*)ctx->plane.p, (uint32_t*)ctx->rowcnt.p };
             LAUNCH(k_dec_alpha, ntiles, 256, 0, al);
             LAUNCH(k_dec_rows_rgba, ntiles, 32, 0, d_tiles, d_imgs, (const DecTile*)d_dt, (const uint32_t*)ctx->rowcnt.p, (RowInfo*)ctx->rows.p);
+            BACK_TO_MAIN();
         }
+        if (lat) LAUNCH(k_dec_rans_v2_lat, 9 * ntiles, 32, lat_smem(LUT_ONE_12), ra, LUT_ONE_12);
+        else LAUNCH(k_dec_rans_v2_small<128>, (9 * ntiles + 127) / 128, 128, 0, ra);
     }
     if (any2) {
         LAUNCH(k_dec_parse_m2, (ntiles + 127) / 128, 128, 0, d_tiles, d_imgs, din, d_dt, ntiles, d_err);
         if (17 * ntiles <= ctx->lat_max_blocks) {
-            RansV1LatArgs la{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 8, LAT_LUT_V1 };
-            FORK_AUX();                               // value streams: side stream, joined before the residual kernels
-            LAUNCH(k_dec_rans_v1_lat, 8 * ntiles, 32, LAT_SMEM_V1, la);
-            BACK_TO_MAIN(); aux_busy = true;
-            la.j0 = 8; la.nj = 9;                     // context streams (and grey planes), then the walk
-            LAUNCH(k_dec_rans_v1_lat, 9 * ntiles, 32, LAT_SMEM_V1, la);
+            // value streams on the side streams (joined before the residual kernels); LAT_M2_ORDER: 0..2 alphabets of at
+            // most 16 symbols (direct table, 64 KiB), 3..7 larger alphabets (two-level), 8..16 contexts, 17 grey plane
+            RansV1LatArgs la{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 3, LUT_ONE_14 };
+            FORK_SIDE(0); side_busy[0] = true;
+            LAUNCH(k_dec_rans_v1_lat, 3 * ntiles, 32, lat_smem(LUT_ONE_14), la);
+            FORK_SIDE(1); side_busy[1] = true;
+            la.j0 = 3; la.nj = 5; la.lut_bytes = LUT_TWO_14;
+            LAUNCH(k_dec_rans_v1_lat, 5 * ntiles, 32, lat_smem(LUT_TWO_14), la);
+            la.j0 = 17; la.nj = 1; la.lut_bytes = LUT_TWO_15;
+            LAUNCH(k_dec_rans_v1_lat, ntiles, 32, lat_smem(LUT_TWO_15), la);
+            BACK_TO_MAIN();
+            la.j0 = 8; la.nj = 9; la.lut_bytes = LUT_TWO_14;   // context streams (two-level tables: they are short), then the walk
+            LAUNCH(k_dec_rans_v1_lat, 9 * ntiles, 32, lat_smem(LUT_TWO_14), la);
         } else {
         RansV1DecArgs rv{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 9, 0, 16 };
         auto k8 = k_dec_rans_v1_small<8, 128>; auto k15 = k_dec_rans_v1_small<15, 128>; auto kbig = k_dec_rans_v1_big<32>;
@@ -663,7 +677,7 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
                       (uint32_t*)ctx->ccnt.p, (uint32_t*)ctx->cbit.p, (uint32_t*)ctx->resv.p, ntiles, d_err };
         LAUNCH(k_dec_chunk_hist, nseg, 256, 0, ch);
         LAUNCH(k_dec_chunk_scan, (ntiles + 3) / 4, 128, 0, ch);
-        if (aux_busy) JOIN_AUX();
+        for (int k = 0; k < 2; k++) if (side_busy[k]) JOIN_SIDE(k);
         if (any1) LAUNCH(k_dec_residuals<1>, nseg, 256, 0, ch);
         if (any2) { LAUNCH(k_dec_residuals<2>, nseg, 256, 0, ch); LAUNCH(k_dec_residuals_grey, nseg, 256, 0, ch); }
         UnpredArgs ua{ d_tiles, d_imgs, d_dt, din, (const uint32_t*)ctx->resv.p, (const uint8_t*)ctx->plane.p, (const RowInfo*)ctx->rows.p,

@@ -24,7 +24,7 @@ namespace xpb {
 // misalignment removed with a funnel shift, zeros past the end: libxpng.c:295, :475), so that the
 // chain reads them with fixed-latency shared loads.  Slot LAT_RING mirrors slot 0 (the chain reads the
 // pair ring[k], ring[k + 1] without wrapping the second index).
-constexpr uint32_t LAT_RING = 2048;              // words; refilled in halves
+constexpr uint32_t LAT_RING = 512;               // words; refilled in halves (a group of 32 symbols consumes at most 32)
 constexpr uint32_t LAT_HALF = LAT_RING / 2;
 constexpr uint32_t LAT_RING_WORDS = LAT_RING + 4;
 
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(32) k_dec_rans_v2_lat(RansDecArgs A, uint32_t 
 // v1 blocks (level 2; libxpng.c:262-301).  Block order: long value streams first, so that the longest
 // chains start in the first wave of CTAs.
 // ---------------------------------------------------------------------------------------------------
-__device__ __constant__ const uint8_t LAT_M2_ORDER[17] = { 12, 13, 11, 14, 15, 16, 10, 9, 0, 1, 2, 3, 4, 5, 6, 7, 8 };   // values first (0..7), contexts (8..16)
+__device__ __constant__ const uint8_t LAT_M2_ORDER[18] = { 12, 11, 9, 13, 14, 15, 16, 10, 0, 1, 2, 3, 4, 5, 6, 7, 8, 0 };   // see the launches in api.cu
 
 struct RansV1LatArgs {
     const TileDesc* tiles;
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(32) k_dec_rans_v1_lat(RansV1LatArgs A) {
     const uint32_t kind = d->m >> 4;
     if (d->m == 0xFE || d->m == 0xFF || d->m == 0 || (kind == 2 && (d->m & 8))) return;
     const bool grey = kind == 2;
-    if (grey && c != 0) return;
+    if (grey != (A.j0 == 17)) return;                 // the grey plane (block 0 of a grey tile) has its own launch
     const uint32_t N = grey ? 256u : (uint32_t)DEC_M2_NSYM[c]; const int pb = grey ? 15 : 14;
     const DecBlock b = d->blk[c];
     const uint8_t* blob = A.in + d->blob_off; const uint8_t* blk = blob + b.off;

@@ -19,58 +19,81 @@ namespace xpb {
 
 constexpr int PAIR_BLK = 16;   // blocks per warp
 
+// Encoder symbol split over two shared arrays so that the recurrence loads ready-to-use words:
+//   EA[sym][PAIR_BLK] = { rcp_freq lo, rcp_freq hi, bias, cmpl_freq }      (ryg-rans Rans64EncSymbol, libxpng.c:331-360)
+//   EB[sym][PAIR_BLK] = { x_max >> 32 = freq << (31 - PROB_BITS), rcp_shift }
+// Row NSYM of both arrays is the identity symbol (rcp = 0, bias = 0, x_max = 2^32 - 1: never renormalises,
+// x' = x), used for the positions past the end of a lane's stream, so the recurrence carries no validity test.
+__device__ __forceinline__ void pair_put_sym(uint4* EA, uint2* EB, uint32_t row, uint32_t blk, uint32_t freq, uint32_t start, int pb) {
+    const uint4 e = make_encsym(freq, start, pb);
+    EA[row * PAIR_BLK + blk] = make_uint4(e.x, e.y, e.z & 0xFFFFu, e.z >> 16);
+    EB[row * PAIR_BLK + blk] = make_uint2((e.w & 0xFFFFu) << (31 - pb), e.w >> 16);
+}
+__device__ __forceinline__ void pair_put_ident(uint4* EA, uint2* EB, uint32_t row, uint32_t blk) {
+    EA[row * PAIR_BLK + blk] = make_uint4(0u, 0u, 0u, 0u);
+    EB[row * PAIR_BLK + blk] = make_uint2(0xFFFFFFFFu, 0u);
+}
+
 // One warp: the 2-lane recurrences of up to 16 blocks.  `live`: this lane's block runs the recurrence.
-// E = &etab[blk] with layout [sym][PAIR_BLK]; row `ident` holds the identity symbol (rcp = 0, bias = 0,
-// freq field 0xFFFF: never renormalises, x' = x), which steps outside the lane's stream use so that the
-// recurrence needs no validity select.  Emission e (0-based) goes to wbase[e] (VER 2) or
-// wbase[-1 - e] (VER 1).  Returns the block's word count; xlo/xhi hold the lane's final state.
-template <int VER>
-__device__ __forceinline__ uint32_t pair_chain(const uint4* E, const uint32_t ident, const int pb, const uint8_t* in, const uint32_t n, const bool live,
-                                               uint32_t* wbase, uint32_t& xlo, uint32_t& xhi) {
-    const uint32_t lane = threadIdx.x & 31, h = lane & 1, bsh = lane & 30u;
+// EA/EB point at the lane's block column.  Emission e (0-based) goes to wbase[e] (VER 2) or wbase[-1 - e]
+// (VER 1).  Returns the block's word count; xlo/xhi hold the lane's final state.
+template <int VER, int NSYM>
+__device__ __forceinline__ uint32_t pair_chain(const uint4* EA, const uint2* EB, const uint8_t* in, const uint32_t n, const bool live, uint32_t* wbase,
+                                               uint32_t& xlo, uint32_t& xhi) {
+    const uint32_t lane = threadIdx.x & 31, h = lane & 1;
+    const uint32_t my = 1u << lane, bsh = lane & 30u;
+    const uint32_t firstm = (VER == 2 ? (1u << (lane & 30u)) : (1u << (lane | 1u))) & ~my;   // the partner's bit when it emits before me
     xlo = 0x80000000u; xhi = 0;                                   // RANS64_L = 2^31
-    auto core = [&](const uint4 e) {                              // state update after the renormalisation decision
+    auto core = [&](const uint4 e, const uint32_t sh) {           // state update after the renormalisation decision
         const uint64_t x = ((uint64_t)xhi << 32) | xlo;
-        const uint64_t q = __umul64hi(x, ((uint64_t)e.y << 32) | e.x) >> (e.w >> 16);
-        const uint64_t y = q * (e.z >> 16) + (x + (e.z & 0xFFFFu));
+        const uint64_t q = __umul64hi(x, ((uint64_t)e.y << 32) | e.x) >> sh;
+        const uint64_t y = q * e.w + (x + e.z);
         xlo = (uint32_t)y; xhi = (uint32_t)(y >> 32);
     };
     const uint32_t nn = VER == 2 ? n : (n & ~1u);                  // v1: the odd tail symbol is coded first, by state 0, without renormalisation
-    if (VER == 1 && live && (n & 1u) && h == 0) core(E[(uint32_t)in[n - 1] * PAIR_BLK]);   // libxpng.c:218-225 (x = 2^31 < x_max: no word)
+    if (VER == 1 && live && (n & 1u) && h == 0) { const uint32_t s = in[n - 1]; core(EA[s * PAIR_BLK], EB[s * PAIR_BLK].y); }   // :218-225
     const uint32_t G = live ? (nn + 15) / 16 : 0;                  // groups of 8 pairs
     uint32_t Gmax = G;
 #pragma unroll
     for (int o = 16; o; o >>= 1) Gmax = max(Gmax, __shfl_xor_sync(0xffffffffu, Gmax, o));
     const uint4* in16 = reinterpret_cast<const uint4*>(in);
+    const char* EAb = reinterpret_cast<const char*>(EA); const char* EBb = reinterpret_cast<const char*>(EB);
     uint32_t wcount = 0, pend_w = 0, pend_bal = 0;
     auto flush = [&]() {                                          // store of the previous step (its ballot is one step old)
-        const uint32_t bits = pend_bal >> bsh, p0 = bits & 1u, p1 = (bits >> 1) & 1u;
-        const uint32_t mine = h ? p1 : p0, before = VER == 2 ? (h ? p0 : 0u) : (h ? 0u : p1);
-        if (mine) { if (VER == 2) wbase[wcount + before] = pend_w; else *(wbase - 1 - (int64_t)(wcount + before)) = pend_w; }
-        wcount += p0 + p1;
+        const uint32_t idx = wcount + ((pend_bal & firstm) ? 1u : 0u);
+        uint32_t* dst = VER == 2 ? wbase + idx : wbase - 1 - (int64_t)idx;
+        // predicated store, never a branch: a divergent branch per step would cost more than the whole recurrence
+        asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.global.u32 [%0], %1;\n}" :: "l"(dst), "r"(pend_w), "r"(pend_bal & my) : "memory");
+        const uint32_t bits = pend_bal >> bsh;                    // no POPC here: its ~20-cycle latency would stall the in-order pipe every step
+        wcount += (bits & 1u) + ((bits >> 1) & 1u);
     };
     uint4 vnext = make_uint4(0, 0, 0, 0);
     if (G) vnext = in16[VER == 2 ? 0 : G - 1];
     for (uint32_t g = 0; g < Gmax; g++) {
         const bool gv = g < G;
         const uint32_t gi = gv ? (VER == 2 ? g : G - 1 - g) : 0u;
-        const uint4 v = vnext;
+        uint4 v = vnext;
         if (g + 1 < G) vnext = in16[VER == 2 ? g + 1 : G - 2 - g];   // the next group's symbols arrive while this group is coded
-        const uint32_t u[4] = { (h ? v.x >> 8 : v.x) & 0x00FF00FFu, (h ? v.y >> 8 : v.y) & 0x00FF00FFu, (h ? v.z >> 8 : v.z) & 0x00FF00FFu,
-                                (h ? v.w >> 8 : v.w) & 0x00FF00FFu };
+        const uint32_t nvalid = gv ? min(16u, nn - 16u * gi) : 0u;     // symbols of this group inside the stream
+        const bool partial = nvalid < 16u;
+        uint32_t vmask = 0xFFFFu;                                    // bit k: symbol k of the group is real
+        if (__any_sync(0xffffffffu, partial)) vmask = (1u << nvalid) - 1u;   // warp-uniform branch, only near stream ends
+        // my eight symbols as row byte offsets into EA (<< 8) : even positions of the group for h = 0, odd for h = 1
+        const uint32_t w4[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
         for (int jj = 0; jj < 8; jj++) {
             const int j = VER == 2 ? jj : 7 - jj;
-            const bool valid = gv && (16u * gi + 2u * j + h) < nn;
-            const uint32_t s = valid ? (u[j >> 1] >> (16 * (j & 1))) & 0xFFu : ident;   // bytes past the stream end are scratch
-            const uint4 e = E[s * PAIR_BLK];
+            const uint32_t word = w4[j >> 1];
+            uint32_t s = (word >> (16 * (j & 1) + 8 * h)) & 0xFFu;
+            s = (vmask >> (2 * j + h)) & 1u ? s : (uint32_t)NSYM;         // past the stream end: identity row
+            const uint4 e = *reinterpret_cast<const uint4*>(EAb + (size_t)s * (PAIR_BLK * 16));
+            const uint2 eb = *reinterpret_cast<const uint2*>(EBb + (size_t)s * (PAIR_BLK * 8));
             flush();
-            const bool p = xhi >= ((e.w & 0xFFFFu) << (31 - pb));            // x >= freq << (63 - pb)  (libxpng.c:370)
+            const bool p = xhi >= eb.x;                               // x >= freq << (63 - pb)  (libxpng.c:370)
             pend_w = xlo;
             pend_bal = __ballot_sync(0xffffffffu, p);
-            const uint32_t olo = p ? xhi : xlo, ohi = p ? 0u : xhi;
-            xlo = olo; xhi = ohi;
-            core(e);
+            xlo = p ? xhi : xlo; xhi = p ? 0u : xhi;
+            core(e, eb.y);
         }
     }
     flush();
@@ -82,9 +105,10 @@ __device__ __forceinline__ uint32_t pair_chain(const uint4* E, const uint32_t id
 // ---------------------------------------------------------------------------------------------------
 template <int NSYM>
 __global__ void __launch_bounds__(32) k_rans_v2_pair(RansV2Args A) {
-    extern __shared__ __align__(16) uint4 etab[];   // [NSYM + 1][PAIR_BLK], last row = identity
+    extern __shared__ __align__(16) uint4 etab[];   // EA[NSYM + 1][PAIR_BLK] then EB[NSYM + 1][PAIR_BLK]; last row = identity
+    uint2* etb = reinterpret_cast<uint2*>(etab + (NSYM + 1) * PAIR_BLK);
     const uint32_t lane = threadIdx.x, h = lane & 1, blk = lane >> 1;
-    if (h == 0) etab[NSYM * PAIR_BLK + blk] = make_uint4(0u, 0u, 0u, 0xFFFFu);
+    if (h == 0) pair_put_ident(etab, etb, NSYM, blk);
     const uint32_t id = blockIdx.x * PAIR_BLK + blk;
     const bool exists = id < A.nc * A.ntiles;
     const uint32_t c = A.c0 + (exists ? id / A.ntiles : 0), tile = exists ? id % A.ntiles : 0;
@@ -109,7 +133,7 @@ __global__ void __launch_bounds__(32) k_rans_v2_pair(RansV2Args A) {
             if (used == 1) { o[0] = 8u | (1u << 24); o[1] = n | ((uint32_t)in[0] << 24); st->bsize[c] = 8; }      // :318
             else {
                 normalise_freqs(F, cum, N, n, pb);
-                for (uint32_t i = 0; i < N; i++) etab[i * PAIR_BLK + blk] = make_encsym(cum[i + 1] - cum[i], cum[i], pb);
+                for (uint32_t i = 0; i < N; i++) pair_put_sym(etab, etb, i, blk, cum[i + 1] - cum[i], cum[i], pb);
                 live = true;
             }
         }
@@ -117,7 +141,7 @@ __global__ void __launch_bounds__(32) k_rans_v2_pair(RansV2Args A) {
     live = __shfl_sync(0xffffffffu, (int)live, lane & 30u) != 0;
     __syncwarp();
     uint32_t xlo, xhi;
-    const uint32_t words = pair_chain<2>(etab + blk, NSYM, pb, in, n, live, o + 3, xlo, xhi);
+    const uint32_t words = pair_chain<2, NSYM>(etab + blk, etb + blk, in, n, live, o + 3, xlo, xhi);
     const uint32_t x1lo = __shfl_sync(0xffffffffu, xlo, lane | 1u), x1hi = __shfl_sync(0xffffffffu, xhi, lane | 1u);
     if (!live || h) return;
     uint32_t* wp = o + 3 + words;
@@ -153,9 +177,10 @@ __global__ void __launch_bounds__(32) k_rans_v2_pair(RansV2Args A) {
 // ---------------------------------------------------------------------------------------------------
 template <int NSYM>
 __global__ void __launch_bounds__(32) k_rans_v1_pair(RansV1Args A) {
-    extern __shared__ __align__(16) uint4 etab[];   // [NSYM + 1][PAIR_BLK], last row = identity
+    extern __shared__ __align__(16) uint4 etab[];   // EA[NSYM + 1][PAIR_BLK] then EB[NSYM + 1][PAIR_BLK]; last row = identity
+    uint2* etb = reinterpret_cast<uint2*>(etab + (NSYM + 1) * PAIR_BLK);
     const uint32_t lane = threadIdx.x, h = lane & 1, blk = lane >> 1;
-    if (h == 0) etab[NSYM * PAIR_BLK + blk] = make_uint4(0u, 0u, 0u, 0xFFFFu);
+    if (h == 0) pair_put_ident(etab, etb, NSYM, blk);
     const uint32_t id = blockIdx.x * PAIR_BLK + blk;
     bool exists = id < A.nc * A.ntiles;
     const uint32_t c = A.c0 + (exists ? id / A.ntiles : 0), tile = exists ? id % A.ntiles : 0;
@@ -200,7 +225,7 @@ __global__ void __launch_bounds__(32) k_rans_v1_pair(RansV1Args A) {
             if (used == 1) { rend[-2] = 8u | (1u << 24); rend[-1] = n | ((uint32_t)in[n - 1] << 24); finish(rend - 2, 1, 0); }   // :169-172
             else {
                 normalise_freqs(F, cum, N, n, pb);
-                for (uint32_t i = 0; i < N; i++) etab[i * PAIR_BLK + blk] = make_encsym(cum[i + 1] - cum[i], cum[i], pb);
+                for (uint32_t i = 0; i < N; i++) pair_put_sym(etab, etb, i, blk, cum[i + 1] - cum[i], cum[i], pb);
                 live = true;
             }
         }
@@ -208,7 +233,7 @@ __global__ void __launch_bounds__(32) k_rans_v1_pair(RansV1Args A) {
     live = __shfl_sync(0xffffffffu, (int)live, lane & 30u) != 0;
     __syncwarp();
     uint32_t xlo, xhi;
-    const uint32_t words = pair_chain<1>(etab + blk, NSYM, pb, in, n, live, rend, xlo, xhi);        // :215-245, words go down from the region end
+    const uint32_t words = pair_chain<1, NSYM>(etab + blk, etb + blk, in, n, live, rend, xlo, xhi);        // :215-245, words go down from the region end
     const uint32_t x1lo = __shfl_sync(0xffffffffu, xlo, lane | 1u), x1hi = __shfl_sync(0xffffffffu, xhi, lane | 1u);
     if (!live || h) return;
     uint32_t* wp = rend - words;
