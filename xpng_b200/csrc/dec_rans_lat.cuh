@@ -45,14 +45,19 @@ struct WordSrc {
     }
     // Stage words [k0, k0 + LAT_HALF) into ring slots (k0 .. ) mod LAT_RING.  All lanes.
     __device__ __forceinline__ void stage(uint32_t* ring, uint32_t k0, uint32_t lane) const {
-        for (uint32_t k = k0 + lane; k < k0 + LAT_HALF; k += 32) {
-            uint32_t v = 0;
-            if (k < nwords) {
-                uint32_t a0, a1;
-                if (DIR > 0) { a0 = __ldg(base + k); a1 = __ldg(base + min(k + 1, jmax)); }
-                else { a0 = __ldg(base - k); a1 = __ldg(base - k + 1); }
-                v = __funnelshift_r(a0, a1, sh);
-            }
+        // all loads first (clamped addresses, no branch), then the stores: one memory latency per call, not one per word
+        uint32_t a0[LAT_HALF / 32], a1[LAT_HALF / 32];
+        const uint32_t kmax = nwords ? nwords - 1 : 0;
+#pragma unroll
+        for (uint32_t i = 0; i < LAT_HALF / 32; i++) {
+            const uint32_t k = min(k0 + lane + 32 * i, kmax);
+            if (DIR > 0) { a0[i] = __ldg(base + k); a1[i] = __ldg(base + min(k + 1, jmax)); }
+            else { a0[i] = __ldg(base - k); a1[i] = __ldg(base - k + 1); }
+        }
+#pragma unroll
+        for (uint32_t i = 0; i < LAT_HALF / 32; i++) {
+            const uint32_t k = k0 + lane + 32 * i;
+            const uint32_t v = k < nwords ? __funnelshift_r(a0[i], a1[i], sh) : 0u;
             const uint32_t slot = k & (LAT_RING - 1);
             ring[slot] = v;
             if (slot == 0) ring[LAT_RING] = v;
@@ -383,7 +388,7 @@ __global__ void __launch_bounds__(32) k_dec_walk_smem(WalkArgs A) {
     const uint32_t* src = walk_sm + myoff;                       // lanes >= 9: nch = 0, src[0] is a valid word
     auto chunk = [&](uint32_t k) -> uint32_t { return k < nch ? src[k] : 0u; };
     uint32_t wlo = chunk(0), whi = chunk(1), cnt = 16, nbuf = chunk(2), ch = 3;
-    uint32_t info = wlo & 0xFu, cur = 0;
+    uint32_t info = wlo & 0xFu, cur = 0, nm = 0, nx = 0;
     uint32_t mk[32];
 #pragma unroll
     for (int j = 0; j < 32; j++) { mk[j] = lane == (uint32_t)j ? 0xFFFFFFFFu : 0u; asm volatile("" : "+r"(mk[j])); }
@@ -402,14 +407,14 @@ __global__ void __launch_bounds__(32) k_dec_walk_smem(WalkArgs A) {
                 // every 8 steps, branch-free: windows at <= 8 symbols append the next 8.  cnt >= 1 holds at every
                 // check (16 at start; a refilled window has >= 9, and at most 8 are popped until the next check),
                 // so `info` is never stale.
-                const uint32_t nm = cnt <= 8u ? 0xFFFFFFFFu : 0u;
+                nm = cnt <= 8u ? 0xFFFFFFFFu : 0u;
                 const unsigned long long add = (unsigned long long)(nbuf & nm) << (4u * min(cnt, 8u));
                 wlo |= (uint32_t)add; whi |= (uint32_t)(add >> 32);
                 cnt += nm & 8u;
-                const uint32_t nx = src[min(ch, nch)];                  // word nch is the zero pad
-                nbuf = (nx & nm) | (nbuf & ~nm);
+                nx = src[min(ch, nch)];                                 // word nch is the zero pad; consumed four steps later
                 ch += nm & 1u;
             }
+            if ((j & 7) == 5) nbuf = (nx & nm) | (nbuf & ~nm);
         }
         if (pos + lane < m) out[pos + lane] = (uint8_t)keep;
     }

@@ -67,13 +67,16 @@ __device__ __forceinline__ uint32_t pair_chain(const uint4* EA, const uint2* EB,
         const uint32_t bits = pend_bal >> bsh;                    // no POPC here: its ~20-cycle latency would stall the in-order pipe every step
         wcount += (bits & 1u) + ((bits >> 1) & 1u);
     };
-    uint4 vnext = make_uint4(0, 0, 0, 0);
+    // symbols are fetched two groups (16 steps, > 1500 cycles) ahead: the load never stalls the in-order pipe
+    uint4 vnext = make_uint4(0, 0, 0, 0), vnext2 = make_uint4(0, 0, 0, 0);
     if (G) vnext = in16[VER == 2 ? 0 : G - 1];
+    if (G > 1) vnext2 = in16[VER == 2 ? 1 : G - 2];
     for (uint32_t g = 0; g < Gmax; g++) {
         const bool gv = g < G;
         const uint32_t gi = gv ? (VER == 2 ? g : G - 1 - g) : 0u;
         uint4 v = vnext;
-        if (g + 1 < G) vnext = in16[VER == 2 ? g + 1 : G - 2 - g];   // the next group's symbols arrive while this group is coded
+        vnext = vnext2;
+        if (g + 2 < G) vnext2 = in16[VER == 2 ? g + 2 : G - 3 - g];
         const uint32_t nvalid = gv ? min(16u, nn - 16u * gi) : 0u;     // symbols of this group inside the stream
         const bool partial = nvalid < 16u;
         uint32_t vmask = 0xFFFFu;                                    // bit k: symbol k of the group is real
