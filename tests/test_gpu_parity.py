@@ -163,6 +163,19 @@ def test_throughput_kernel_family(monkeypatch):
             assert cd.encode(lv, imgs) == want
             for b, im in zip(cd.decode(want), imgs):
                 assert np.array_equal(b, po.normalize(im))
+        # corrupt files through this family as well: failure or garbage, never a fault
+        rng = np.random.default_rng(11)
+        for lv, img in ((1, imgs[1]), (2, imgs[0])):
+            good = po.encode(lv, img)
+            for k in range(16):
+                f = bytearray(good)
+                for _ in range(int(rng.integers(1, 6))):
+                    f[int(rng.integers(8, len(f)))] = int(rng.integers(0, 256))
+                try:
+                    cd.decode([bytes(f)])
+                except RuntimeError:
+                    pass
+            assert np.array_equal(cd.decode([good])[0], po.normalize(img))
     finally:
         cd.close()
 

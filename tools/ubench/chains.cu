@@ -125,6 +125,94 @@ __global__ void k_dec_d2one(const uint32_t* lut_g, const uint32_t* words, uint32
 }
 
 
+
+// D4: as D2, but chain B is skewed by half a round in program order: B's table lookup is issued before A's
+// multiply, and B's multiply before A's renormalisation.
+__global__ void k_dec_d4(const uint32_t* lut_g, const uint32_t* words, uint32_t nwords, uint32_t n, int pb, uint8_t* out, long long* cyc) {
+    extern __shared__ uint32_t sm[];
+    uint32_t* lut = sm; uint32_t* ring = sm + (1u << pb);
+    const uint32_t lane = threadIdx.x;
+    for (uint32_t i = lane; i < (1u << pb); i += 32) lut[i] = lut_g[i];
+    for (uint32_t i = lane; i < RING + 8; i += 32) ring[i] = words[(i % RING) % nwords];
+    __syncwarp();
+    const uint32_t mask = (1u << pb) - 1u;
+    uint32_t alo = 0x12345678u, ahi = 0x1u, blo = 0x9abcdef0u, bhi = 0x2u, kb = 0;
+    uint32_t mk[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) { mk[j] = lane == (uint32_t)j ? 0xFFFFFFFFu : 0u; asm volatile("" : "+r"(mk[j])); }
+    const char* ringb = reinterpret_cast<const char*>(ring);
+    long long t0 = clock64();
+    // prologue: A's lookup
+    uint32_t ea = lut[alo & mask];
+    for (uint32_t i = 0; i + 32 <= n; i += 32) {
+        uint32_t keep = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            // B lookup issued first (its state is final since the previous round)
+            const uint32_t eb = lut[blo & mask];
+            // A multiply + renorm (word = ring[kb])
+            {   const uint32_t c0 = *reinterpret_cast<const uint32_t*>(ringb + kb);
+                const uint32_t qlo = __funnelshift_r(alo, ahi, pb), qhi = ahi >> pb, f = ea >> 18, b = ea & 0x3FFFu;
+                const unsigned long long t = (unsigned long long)f * qlo + b; alo = (uint32_t)t; ahi = f * qhi + (uint32_t)(t >> 32);
+                const bool pa = (ahi | (alo & 0x80000000u)) == 0;
+                ahi = pa ? alo : ahi; alo = pa ? c0 : alo; kb = (kb + (pa ? 4u : 0u)) & (RING * 4 - 1); }
+            keep |= ea & mk[j];
+            // A's next lookup
+            ea = lut[alo & mask];
+            // B multiply + renorm
+            {   const uint32_t c0 = *reinterpret_cast<const uint32_t*>(ringb + kb);
+                const uint32_t qlo = __funnelshift_r(blo, bhi, pb), qhi = bhi >> pb, f = eb >> 18, b = eb & 0x3FFFu;
+                const unsigned long long t = (unsigned long long)f * qlo + b; blo = (uint32_t)t; bhi = f * qhi + (uint32_t)(t >> 32);
+                const bool pq = (bhi | (blo & 0x80000000u)) == 0;
+                bhi = pq ? blo : bhi; blo = pq ? c0 : blo; kb = (kb + (pq ? 4u : 0u)) & (RING * 4 - 1); }
+            keep |= eb & mk[j + 1];
+        }
+        out[i + lane] = (uint8_t)((keep >> 14) & 15u);
+    }
+    long long t1 = clock64();
+    if (lane == 0) { cyc[0] = t1 - t0; out[n] = (uint8_t)(alo + blo + ahi + bhi + ea); }
+}
+
+
+// D5: pair-SIMT decode: even lanes own state A, odd lanes state B (one instruction stream for both);
+// a ballot per round tells everyone who renormalised; B's word is ring[k + pA].
+template <int SPEC>
+__global__ void k_dec_d5(const uint32_t* lut_g, const uint32_t* words, uint32_t nwords, uint32_t n, int pb, uint8_t* out, long long* cyc) {
+    extern __shared__ uint32_t sm[];
+    uint32_t* lut = sm; uint32_t* ring = sm + (1u << pb);
+    const uint32_t lane = threadIdx.x, h = lane & 1;
+    for (uint32_t i = lane; i < (1u << pb); i += 32) lut[i] = lut_g[i];
+    for (uint32_t i = lane; i < RING + 8; i += 32) ring[i] = words[(i % RING) % nwords];
+    __syncwarp();
+    const uint32_t mask = (1u << pb) - 1u;
+    uint32_t xlo = h ? 0x9abcdef0u : 0x12345678u, xhi = h ? 0x2u : 0x1u, kb = 0;
+    uint32_t mk[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) { mk[j] = (lane >> 1) == (uint32_t)j ? 0xFFFFFFFFu : 0u; asm volatile("" : "+r"(mk[j])); }
+    const char* ringb = reinterpret_cast<const char*>(ring);
+    long long t0 = clock64();
+    for (uint32_t i = 0; i + 32 <= n; i += 32) {
+        uint32_t keep = 0;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const uint32_t c0 = *reinterpret_cast<const uint32_t*>(ringb + kb), c1 = *reinterpret_cast<const uint32_t*>(ringb + kb + 4);
+            const uint32_t slot = xlo & mask; const uint32_t e = lut[slot];
+            const uint32_t qlo = __funnelshift_r(xlo, xhi, pb), qhi = xhi >> pb, f = e >> 18, b = e & 0x3FFFu;
+            const unsigned long long t = (unsigned long long)f * qlo + b; const uint32_t lo = (uint32_t)t, hi = f * qhi + (uint32_t)(t >> 32);
+            const bool p = (hi | (lo & 0x80000000u)) == 0;
+            const uint32_t bal = __ballot_sync(0xffffffffu, p);
+            const uint32_t pa = bal & 1u, pq = (bal >> 1) & 1u;
+            const uint32_t w = (h & pa) ? c1 : c0;
+            xhi = p ? lo : hi; xlo = p ? w : lo;
+            kb = (kb + 4u * (pa + pq)) & (RING * 4 - 1);
+            keep |= e & mk[j];
+        }
+        out[i + lane] = (uint8_t)((keep >> 14) & 15u);
+    }
+    long long t1 = clock64();
+    if (lane < 2) { cyc[0] = t1 - t0; out[n + lane] = (uint8_t)(xlo + xhi); }
+}
+
 // D3: the renormalisation predicate comes from a second table: x' = f*q + b < 2^31  <=>  qhi == 0 && qlo <= T[slot],
 // T[slot] = floor((2^31 - 1 - b) / f): the predicate no longer waits for the 64-bit multiply, and the next slot only
 // needs the LOW word of x' (a 32-bit IMAD).
@@ -925,6 +1013,14 @@ int main() {
         cudaFuncSetAttribute(k_dec_d3, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * sm + 64);
         for (int r = 0; r < 2; r++) { k_dec_d3<<<1, 32, 2 * sm + 64>>>(d_lut, d_lutT, d_words, 4096, n, pb, d_out, cyc); cudaDeviceSynchronize(); }
         cudaMemcpy(o3.data(), d_out, n, cudaMemcpyDeviceToHost);
+        { std::vector<uint8_t> o4(n);
+          for (int r = 0; r < 2; r++) { k_dec_d4<<<1, 32, sm + 64>>>(d_lut, d_words, 4096, n, pb, d_out, cyc); cudaDeviceSynchronize(); }
+          cudaMemcpy(o4.data(), d_out, n, cudaMemcpyDeviceToHost);
+          printf("dec_d4 (skewed)      %7.2f cycles/symbol %s\n", (double)cyc[0] / n, o4 == o2 ? "same symbols as d2" : "MISMATCH vs d2"); }
+        { std::vector<uint8_t> o5(n);
+          for (int r = 0; r < 2; r++) { k_dec_d5<0><<<1, 32, sm + 64>>>(d_lut, d_words, 4096, n, pb, d_out, cyc); cudaDeviceSynchronize(); }
+          cudaMemcpy(o5.data(), d_out, n, cudaMemcpyDeviceToHost);
+          printf("dec_d5 (pair SIMT)   %7.2f cycles/symbol %s\n", (double)cyc[0] / n, o5 == o2 ? "same symbols as d2" : "MISMATCH vs d2"); }
         printf("dec_d3 (pred table)  %7.2f cycles/symbol %s\n", (double)cyc[0] / n, o2 == o3 ? "same symbols as d2" : "MISMATCH vs d2"); }
     for (int r = 0; r < 2; r++) { k_issue<<<1, 32>>>((uint32_t*)d_out, cyc, 5); cudaDeviceSynchronize(); }
     printf("issue 8 indep (xor,add)   %7.2f cycles per 16 ops (SASS-count dependent)\n", (double)cyc[0] / 4096);

@@ -344,7 +344,8 @@ static int encode_chunk(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32_t n
         memcpy(ctx->pin_a.p, S.imgs.data(), nb);
         CK(cudaMemcpyAsync(ctx->imgs.p, ctx->pin_a.p, nb, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemsetAsync(ctx->flags.p, 0, n * 4, ctx->stream));
-        LAUNCH(k_image_scan, dim3(64, n), 256, 0, (const ImageDesc*)ctx->imgs.p, (uint32_t*)ctx->flags.p);
+        const unsigned scan_chunks = n >= 148 ? 8u : (1184u / n > 592u ? 592u : 1184u / n);   // ~8 CTAs per SM over the whole batch
+        LAUNCH(k_image_scan, dim3(scan_chunks, n), 256, 0, (const ImageDesc*)ctx->imgs.p, (uint32_t*)ctx->flags.p);
         CK(cudaMemcpyAsync(flags.data(), ctx->flags.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         // apply normalisation (libxpng.c:688-721)
@@ -597,9 +598,17 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
     const uint32_t ntiles = (uint32_t)P.tiles.size();
     if (upload_plan(ctx, P)) return 1;
     ENSURE(dimgs, n * sizeof(DecImage)); ENSURE(dtiles, ntiles * sizeof(DecTile)); ENSURE(errflag, 4);
-    if (ensure_pin(ctx, ctx->pin_b, n * sizeof(DecImage) + 64)) return 1;
+    if (ensure_pin(ctx, ctx->pin_b, n * (sizeof(DecImage) + 8) + 64)) return 1;
     memcpy(ctx->pin_b.p, DI.data(), n * sizeof(DecImage));
     CK(cudaMemcpyAsync(ctx->dimgs.p, ctx->pin_b.p, n * sizeof(DecImage), cudaMemcpyHostToDevice, ctx->stream));
+    bool any7 = false;
+    for (uint32_t i = 0; i < n; i++) any7 |= DI[i].mode == 7;
+    if (any7) {   // where each stored image's file starts (k_load7), ~0 = not a stored image
+        uint64_t* cf = (uint64_t*)((uint8_t*)ctx->pin_b.p + n * sizeof(DecImage));
+        for (uint32_t i = 0; i < n; i++) cf[i] = DI[i].mode == 7 ? DI[i].file_off : ~0ull;
+        ENSURE(offs, n * 8);
+        CK(cudaMemcpyAsync(ctx->offs.p, cf, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
     CK(cudaMemsetAsync(ctx->errflag.p, 0, 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->dtiles.p, 0, ntiles * sizeof(DecTile), ctx->stream));
     const TileDesc* d_tiles = (const TileDesc*)ctx->tiles.p;
@@ -685,6 +694,7 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
         LAUNCH(k_dec_unpredict, ntiles, UNP_THREADS, 0, ua);
         if (any2) LAUNCH(k_dec_grey_raw, ntiles, 256, 0, d_tiles, d_imgs, (const DecTile*)d_dt, din);
     }
+    if (any7) LAUNCH(k_load7, dim3(296, n), 256, 0, (const ImageDesc*)ctx->imgs.p, (const uint64_t*)ctx->offs.p, din);   // stored images: flat copies
     LAUNCH(k_dec_copy, ntiles, 256, 0, d_tiles, d_imgs, (const DecTile*)d_dt, din, (uint8_t*)nullptr);
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     int herr = 0;

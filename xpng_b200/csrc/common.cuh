@@ -126,6 +126,18 @@ __device__ __forceinline__ void st32u(uint8_t* p, uint32_t v) {
 }
 __device__ __forceinline__ uint64_t ld64u(const uint8_t* p) { return (uint64_t)ld32u(p) | ((uint64_t)ld32u(p + 4) << 32); }
 
+// Four consecutive RGB pixels (12 bytes) at ANY byte alignment as 0x00BBGGRR each: four aligned 32-bit loads and
+// three funnel shifts instead of twelve byte loads.  Touches the aligned words covering p .. p + 15 (callers keep
+// 4 bytes of slack; every pixel buffer of the codec has it).
+__device__ __forceinline__ void ld_rgb4(const uint8_t* p, uint32_t px[4]) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+    const uint32_t a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2), a3 = __ldg(q + 3);
+    const uint32_t w0 = __funnelshift_r(a0, a1, sh), w1 = __funnelshift_r(a1, a2, sh), w2 = __funnelshift_r(a2, a3, sh);
+    px[0] = w0 & 0xFFFFFFu; px[1] = (w0 >> 24) | ((w1 & 0xFFFFu) << 8); px[2] = (w1 >> 16) | ((w2 & 0xFFu) << 16); px[3] = w2 >> 8;
+}
+
 // Load one pixel as 0x00BBGGRR / 0xAABBGGRR.
 template <int PXSZ>
 __device__ __forceinline__ uint32_t ld_pixel(const uint8_t* p) {

@@ -105,15 +105,16 @@ __device__ __forceinline__ bool v1_block_setup(const RansV1DecArgs& A, uint32_t 
     B.blob = A.in + d->blob_off; B.blk = B.blob + b.off; B.out = A.streams + t.str_off + b.soff;
     B.n = b.n; B.type = b.type; B.bitpos = d->bitpos[c]; B.bsz = d->bsz; B.bsize = ld32u(B.blk) & 0xFFFFFFu;
     if (B.type == 0 || B.n == 0) return false;
+    const bool ctx = !grey && c < 9;   // context streams: symbols above 8 (corrupt data) are stored as 0, the walk indexes lanes by them
     if (B.type == 1) {
-        const uint32_t v4 = (ld32u(B.blk + 4) >> 24) * 0x01010101u;
+        const uint32_t v1 = ld32u(B.blk + 4) >> 24, v4 = (ctx && v1 > 8u ? 0u : v1) * 0x01010101u;
         for (uint32_t k = 0; k < (B.n + 3) / 4; k++) reinterpret_cast<uint32_t*>(B.out)[k] = v4;
         return false;
     }
     if (B.type == 2) {
         BitR r{ B.blob + 8, B.blob + 4 + B.bsz, B.bitpos };
         const uint32_t nbit = bitlen32(B.N - 1);
-        for (uint32_t k = 0; k < B.n; k++) B.out[k] = (uint8_t)r.get(nbit);
+        for (uint32_t k = 0; k < B.n; k++) { const uint32_t v = r.get(nbit); B.out[k] = (uint8_t)(ctx && v > 8u ? 0u : v); }
         return false;
     }
     return true;

@@ -144,14 +144,16 @@ __global__ void __launch_bounds__(LANES) k_dec_rans_v2_small(RansDecArgs A) {
     if (b.type == 0 || n == 0) return;
     const uint32_t w1 = ld32u(blk + 4), v2 = w1 >> 24;
     const uint32_t csz = ld32u(blk) & 0xFFFFFFu;
+    // this kernel only decodes context streams (c < 9): symbols above 8 can only come from corrupt data and are
+    // stored as 0, because the context walk uses them as lane indices
     if (b.type == 1) {   // run of one symbol
-        const uint32_t v4 = v2 * 0x01010101u;
+        const uint32_t v4 = (v2 > 8u ? 0u : v2) * 0x01010101u;
         for (uint32_t k = 0; k < (n + 3) / 4; k++) reinterpret_cast<uint32_t*>(out)[k] = v4;
         return;
     }
     if (b.type == 2) {   // plain v2-bit symbols
         BitR r{ blk + 8, blk + csz, 0 };
-        for (uint32_t k = 0; k < n; k++) out[k] = (uint8_t)r.get(v2);
+        for (uint32_t k = 0; k < n; k++) { const uint32_t v = r.get(v2); out[k] = (uint8_t)(v > 8u ? 0u : v); }
         return;
     }
     const uint32_t N = v2 + 2, w2 = ld32u(blk + 8); const int pb = (int)(w2 >> 24);
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(LANES) k_dec_rans_v2_small(RansDecArgs A) {
         const uint32_t e = fs[s * LANES + threadIdx.x];
         x = (uint64_t)(e >> 16) * (x >> pb) + slot - (e & 0xFFFFu);
         XPB_RENORM_BACK(x)
-        return s;
+        return s > 8u ? 0u : s;
     };
     int64_t i = (int64_t)n - 1;
     // head: until (i + 1) is a multiple of 4
@@ -264,9 +266,8 @@ __global__ void __launch_bounds__(LANES) k_dec_rans_v2_big(RansDecArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Context walk: nl_{i+1} = next unread symbol of stream nl_i.  Inherently serial per tile; one lane
-// per tile, each stream buffered as a 64-bit window of 4-bit symbols in shared memory
-// ([stream][lane] layout, conflict-free), refilled 8 symbols at a time from the byte streams.
+// Context walk: nl_{i+1} = next unread symbol of stream nl_i.  Inherently serial per tile; the kernels
+// (k_dec_walk_smem, k_dec_walk_lat) live in dec_rans_lat.cuh, this is their argument block.
 // ------------------------------------------------------------------------------------------------
 struct WalkArgs {
     const TileDesc* tiles;
@@ -277,74 +278,6 @@ struct WalkArgs {
     uint32_t ntiles;
     uint32_t mode;
 };
-
-__device__ __forceinline__ unsigned long long pack8_nibbles(unsigned long long v) {
-    unsigned long long x = v & 0x0F0F0F0F0F0F0F0Full;
-    x = (x | (x >> 4)) & 0x00FF00FF00FF00FFull;
-    x = (x | (x >> 8)) & 0x0000FFFF0000FFFFull;
-    x = (x | (x >> 16)) & 0x00000000FFFFFFFFull;
-    return x;
-}
-
-// Warp-cooperative walk.  One warp per tile; lane c < 9 owns stream c: a 64-bit window of sixteen
-// 4-bit symbols in registers, the next sixteen prefetched.  Every lane tracks the current context
-// `nl` (uniform), so the only thing on the dependent chain is one shuffle per MACRO step: lane c
-// publishes, for its window, the length r of the leading run of self-transitions (symbols == c) and
-// the first symbol e that leaves the context; one macro step emits r copies of c followed by e.
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_dec_walk(WalkArgs A) {
-    const uint32_t tile = blockIdx.x * WARPS + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (tile >= A.ntiles) return;
-    const TileDesc t = A.tiles[tile];
-    if (A.imgs[t.img].mode != A.mode) return;
-    const DecTile* d = A.dt + tile;
-    if (d->m == 0 || d->m >= 0x20) return;   // raw / grey / single colour / failed
-    uint8_t* out = A.nlseq + t.px_off;
-    const uint32_t m = d->nsym;
-    // per-lane stream state (lanes >= 9 own an empty stream)
-    const uint32_t c = lane < 9 ? lane : 0;
-    const uint32_t n = lane < 9 ? d->blk[c].n : 0;
-    const uint4* src = reinterpret_cast<const uint4*>(A.streams + t.str_off + d->blk[c].soff);
-    auto pack16 = [](uint4 q) -> unsigned long long {
-        const unsigned long long lo = pack8_nibbles((unsigned long long)q.x | ((unsigned long long)q.y << 32));
-        const unsigned long long hi = pack8_nibbles((unsigned long long)q.z | ((unsigned long long)q.w << 32));
-        return lo | (hi << 32);
-    };
-    uint32_t taken = 0;                      // symbols of my stream already moved into `win`
-    unsigned long long win = 0, nxt = 0; uint32_t cnt = 0;
-    if (n) { win = pack16(src[0]); cnt = n < 16 ? n : 16; taken = cnt; if (n > 16) nxt = pack16(src[1]); }
-    const unsigned long long selfpat = 0x1111111111111111ull * c;
-    auto publish = [&]() -> uint32_t {       // r | e << 5 | has_e << 9
-        if (cnt == 0) return (1u << 9);      // exhausted (corrupt data): endless zeros
-        const unsigned long long x = win ^ selfpat;
-        uint32_t r = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 2 : 16u;
-        if (r > cnt) r = cnt;
-        uint32_t info = r;
-        if (r < cnt) { uint32_t e = (uint32_t)(win >> (4 * r)) & 15u; if (e > 8) e = 0; info |= (e << 5) | (1u << 9); }
-        return info;
-    };
-    uint32_t info = publish();
-    uint32_t nl = 0, pos = 0;
-    while (pos < m) {
-        const uint32_t got = __shfl_sync(0xffffffffu, info, nl);
-        uint32_t r = got & 31u; const uint32_t has_e = (got >> 9) & 1u, e = (got >> 5) & 15u;
-        if (r + has_e > m - pos) { r = min(r, m - pos); }
-        const uint32_t k = min(r + has_e, m - pos);
-        if (lane < k) out[pos + lane] = (uint8_t)(lane < r ? nl : e);
-        if (lane == nl) {                    // pop k symbols from my window
-            if (cnt) {
-                win = k >= 16 ? 0ull : (win >> (4 * k)); cnt -= min(k, cnt);
-                if (cnt == 0 && taken < n) {
-                    win = nxt; cnt = n - taken < 16 ? n - taken : 16; taken += cnt;
-                    if (taken < n) nxt = pack16(src[taken >> 4]);
-                }
-            }
-            info = publish();
-        }
-        pos += k;
-        if (has_e) nl = e;
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // Alpha plane (RGBA): un-zig-zag + prefix sums (column 0 down, then along each row), per-row counts
@@ -423,12 +356,7 @@ __global__ void __launch_bounds__(256) k_dec_copy(const TileDesc* tiles, const D
     const DecImage I = imgs[t.img];
     uint8_t* dst = px + t.src_off;
     const uint32_t rowb = t.w * t.pxsz;
-    if ((I.mode & 0xFF) == 7) {
-        const uint8_t* src = in + I.file_off + 8 + (uint64_t)t.y0 * t.bpr + (uint64_t)t.x0 * t.pxsz;
-        for (uint32_t y = threadIdx.x >> 5; y < t.h; y += 8)
-            for (uint32_t k = threadIdx.x & 31; k < rowb; k += 32) dst[(uint64_t)y * t.bpr + k] = src[(uint64_t)y * t.bpr + k];
-        return;
-    }
+    if ((I.mode & 0xFF) == 7) return;   // stored images are copied by k_load7
     if (I.mode & 0x100) {   // libxpng.c:976-980
         const uint8_t* col = in + I.file_off + 8;
         for (uint32_t y = threadIdx.x >> 5; y < t.h; y += 8)

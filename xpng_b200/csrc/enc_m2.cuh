@@ -19,9 +19,15 @@ __global__ void __launch_bounds__(256) k_m2_classify(const TileDesc* __restrict_
     const uint8_t* src = reinterpret_cast<const uint8_t*>(t.src_off);
     const uint32_t f0 = src[0], f1 = src[1], f2 = src[2];
     int single = 1, grey = 1;
+    const uint32_t first = f0 | (f1 << 8) | (f2 << 16), wq = 3 * t.w >= 16 ? (3 * t.w - 16) / 12 + 1 : 0;   // 16-byte windows inside the row
     for (uint32_t y = threadIdx.x >> 5; y < t.h; y += 8) {
         const uint8_t* row = src + (uint64_t)y * t.bpr;
-        for (uint32_t x = threadIdx.x & 31; x < t.w; x += 32) {
+        for (uint32_t g = threadIdx.x & 31; g < wq; g += 32) {           // four pixels per lane and iteration (ld_rgb4)
+            uint32_t v[4]; ld_rgb4(row + 12 * g, v);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { single &= v[k] == first; grey &= v[k] == (v[k] & 0xFFu) * 0x010101u; }
+        }
+        for (uint32_t x = (wq << 2) + (threadIdx.x & 31); x < t.w; x += 32) {
             const uint32_t a = row[3 * x], b = row[3 * x + 1], c = row[3 * x + 2];
             single &= (a == f0) & (b == f1) & (c == f2);
             grey &= (a == b) & (b == c);

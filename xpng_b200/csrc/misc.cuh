@@ -26,7 +26,13 @@ __global__ void __launch_bounds__(256) k_image_scan(const ImageDesc* __restrict_
         }
     } else {
         const uint32_t first = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16);
-        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t nq = 3 * npx >= 16 ? (3 * npx - 16) / 12 + 1 : 0;   // groups of four pixels whose 16-byte window stays inside the image
+        for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < nq; g += (uint64_t)gridDim.x * blockDim.x) {
+            uint32_t v[4]; ld_rgb4(p + 12 * g, v);
+            if ((v[0] != first) | (v[1] != first) | (v[2] != first) | (v[3] != first)) f |= SCAN_NOT_SINGLE;
+        }
+        if (blockIdx.x == 0 && (nq << 2) + threadIdx.x < npx) {  // tail (at most 7 pixels)
+            const uint64_t i = (nq << 2) + threadIdx.x;
             const uint32_t v = (uint32_t)p[3 * i] | ((uint32_t)p[3 * i + 1] << 8) | ((uint32_t)p[3 * i + 2] << 16);
             if (v != first) f |= SCAN_NOT_SINGLE;
         }
@@ -65,6 +71,21 @@ __global__ void __launch_bounds__(256) k_store7(const ImageDesc* __restrict__ im
     unsigned long long* d8 = reinterpret_cast<unsigned long long*>(file + 8);
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (uint64_t)gridDim.x * blockDim.x) d8[i] = s8[i];
     if (blockIdx.x == 0) for (uint64_t i = (nw << 3) + threadIdx.x; i < I.raw_size; i += blockDim.x) file[8 + i] = src[i];
+}
+
+// Stored file -> pixels (level 7 decode, libxpng.c:974): a flat copy.  grid = (chunks, nimg); only images with
+// copy_from[i] != ~0 are copied (byte offset of the file inside `in`).  Source (file + 8) is 8-aligned.
+__global__ void __launch_bounds__(256) k_load7(const ImageDesc* __restrict__ imgs, const uint64_t* __restrict__ copy_from, const uint8_t* __restrict__ in) {
+    const uint64_t from = copy_from[blockIdx.y];
+    if (from == ~0ull) return;
+    const ImageDesc I = imgs[blockIdx.y];
+    uint8_t* dst = reinterpret_cast<uint8_t*>(I.px_off);
+    const uint8_t* src = in + from + 8;
+    const uint64_t nw = I.raw_size >> 3;
+    const unsigned long long* s8 = reinterpret_cast<const unsigned long long*>(src);
+    unsigned long long* d8 = reinterpret_cast<unsigned long long*>(dst);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (uint64_t)gridDim.x * blockDim.x) d8[i] = __ldg(s8 + i);
+    if (blockIdx.x == 0) for (uint64_t i = (nw << 3) + threadIdx.x; i < I.raw_size; i += blockDim.x) dst[i] = src[i];
 }
 
 // First two header words of n files -> hdr[n][2]
