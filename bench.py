@@ -304,10 +304,22 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_src = peaks()
     alg_bytes = raw + xpng_bytes[top_lv] if top_lv != 7 else 2 * raw
     achieved = alg_bytes / 1e9 / (top_ms / 1e3)
+    # DRAM traffic of that kernel from the committed `ncu --set full` capture (profiles/r01_traffic.json), per launch
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        key = {"k_rans_v1_pair_16": "k_rans_v1_pair<16>", "k_rans_v2_pair_16": "k_rans_v2_pair<16>", "k_dec_walk_smem<0>": "k_dec_walk_smem<0>",
+               "k_dec_rans_v1_lat_values16": "k_dec_rans_v1_lat", "k_dec_rans_v2_lat": "k_dec_rans_v2_lat"}.get(top_name.split(".")[-1])
+        for name, rec in tj.items():
+            if key and key in name:
+                traffic = int(rec["dram_read_bytes"] + rec["dram_write_bytes"]); traffic_src = "profiles/" + rec["report"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": top_name, "kernel_ms": round(top_ms, 4), "achieved": round(achieved, 2), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "dominant kernel is a per-tile serial chain (rANS state / context walk): latency-bound, see DESIGN.md"}
+                "note": "dominant kernel is a serial chain fixed by the bit stream (2 rANS states per entropy block): one 4K frame is "
+                        "latency-bound, 48 warps on 148 SMs; see DESIGN.md section 3 and 6, profiles/r01_ncu_summaries.md"}
     # ---- whole-step roofline view: algorithmic bytes of all 6 calls over the step time
     step_bytes = sum((raw + xpng_bytes[lv]) if lv != 7 else 2 * raw for lv in LEVELS) * 2
     breakdown["step_algorithmic_GB_s"] = round(step_bytes / 1e9 / (ms_dev / args.steps / 1e3), 2)

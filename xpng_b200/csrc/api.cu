@@ -210,22 +210,22 @@ static int m2_encode_tiles(xpngb_ctx* ctx, const Plan& P, uint32_t ntiles, uint3
     RansV1Args ra{ d_tiles, (TileState*)ctx->state.p, (const uint32_t*)ctx->hist.p, (const uint8_t*)ctx->tclass.p,
                    (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->blocks.p, (uint32_t*)ctx->tabs.p, ntiles, 0, 17, 0, 0 };
     if (17 * ntiles <= ctx->lat_max_blocks) {
-        auto p_small = k_rans_v1_pair<16>; auto p_big = k_rans_v1_pair<256>;
+        auto k_rans_v1_pair_16 = k_rans_v1_pair<16>; auto k_rans_v1_pair_256 = k_rans_v1_pair<256>;
         FORK_SIDE(0);                                 // alphabets above 16 symbols and the grey candidates: side stream
         RansV1Args rb = ra; rb.c0 = 9; rb.nc = 8; rb.nmin = 16;
-        LAUNCH(p_big, (8 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, rb);
+        LAUNCH(k_rans_v1_pair_256, (8 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, rb);
         rb.c0 = 0; rb.nc = 4; rb.nmin = 0; rb.grey = 1;
-        LAUNCH(p_big, (4 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, rb);
+        LAUNCH(k_rans_v1_pair_256, (4 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, rb);
         BACK_TO_MAIN();
-        LAUNCH(p_small, (17 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 17 * PAIR_BLK * 24, ra);
+        LAUNCH(k_rans_v1_pair_16, (17 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 17 * PAIR_BLK * 24, ra);
         JOIN_SIDE(0);
     } else {
-    auto k_small = k_rans_v1<16, 128>; auto k_big = k_rans_v1<256, 32>;
-    LAUNCH(k_small, (17 * ntiles + 127) / 128, 128, 16 * 128 * 16, ra);
+    auto k_rans_v1_lane_16 = k_rans_v1<16, 128>; auto k_rans_v1_lane_256 = k_rans_v1<256, 32>;
+    LAUNCH(k_rans_v1_lane_16, (17 * ntiles + 127) / 128, 128, 16 * 128 * 16, ra);
     ra.c0 = 9; ra.nc = 8; ra.nmin = 16;
-    LAUNCH(k_big, (8 * ntiles + 31) / 32, 32, 256 * 32 * 16, ra);
+    LAUNCH(k_rans_v1_lane_256, (8 * ntiles + 31) / 32, 32, 256 * 32 * 16, ra);
     ra.c0 = 0; ra.nc = 4; ra.nmin = 0; ra.grey = 1;
-    LAUNCH(k_big, (4 * ntiles + 31) / 32, 32, 256 * 32 * 16, ra);
+    LAUNCH(k_rans_v1_lane_256, (4 * ntiles + 31) / 32, 32, 256 * 32 * 16, ra);
     }
     LAUNCH(k_m2_finish, (ntiles + 127) / 128, 128, 0, d_tiles, (const uint8_t*)ctx->tclass.p, (TileState*)ctx->state.p, ntiles);
     return 0;
@@ -428,15 +428,15 @@ static int encode_chunk(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32_t n
         RansV2Args ra{ d_tiles, (TileState*)ctx->state.p, (uint32_t*)ctx->hist.p, (const uint8_t*)ctx->streams.p,
                        (const uint8_t*)ctx->alpha.p, (uint8_t*)ctx->blocks.p, ntiles, 0, 9 };
         if (9 * ntiles <= ctx->lat_max_blocks) {
-            auto p_small = k_rans_v2_pair<16>; auto p_big = k_rans_v2_pair<256>;
-            LAUNCH(p_small, (9 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 17 * PAIR_BLK * 24, ra);
-            if (P.any_rgba) { ra.c0 = 9; ra.nc = 1; LAUNCH(p_big, (ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, ra); }
+            auto k_rans_v2_pair_16 = k_rans_v2_pair<16>; auto k_rans_v2_pair_256 = k_rans_v2_pair<256>;
+            LAUNCH(k_rans_v2_pair_16, (9 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 17 * PAIR_BLK * 24, ra);
+            if (P.any_rgba) { ra.c0 = 9; ra.nc = 1; LAUNCH(k_rans_v2_pair_256, (ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, ra); }
         } else {
-        auto k_small = k_rans_v2<9, 128>; auto k_big = k_rans_v2<256, 32>;
-        LAUNCH(k_small, (9 * ntiles + 127) / 128, 128, 9 * 128 * 16, ra);
+        auto k_rans_v2_lane_9 = k_rans_v2<9, 128>; auto k_rans_v2_lane_256 = k_rans_v2<256, 32>;
+        LAUNCH(k_rans_v2_lane_9, (9 * ntiles + 127) / 128, 128, 9 * 128 * 16, ra);
         if (P.any_rgba) {
             ra.c0 = 9; ra.nc = 1;
-            LAUNCH(k_big, (ntiles + 31) / 32, 32, 256 * 32 * 16, ra);
+            LAUNCH(k_rans_v2_lane_256, (ntiles + 31) / 32, 32, 256 * 32 * 16, ra);
         }
         }
     }
@@ -633,7 +633,8 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
         if (P.any_rgba) {                             // the alpha plane is independent of the context walk: side stream
             FORK_SIDE(1); side_busy[1] = true;
             RansDecArgs rb = ra; rb.c0 = 9; rb.nc = 1;
-            if (lat) LAUNCH(k_dec_rans_v2_lat, ntiles, 32, lat_smem(LUT_TWO_15), rb, LUT_TWO_15);
+            auto k_dec_rans_v2_lat_alpha = k_dec_rans_v2_lat;
+            if (lat) LAUNCH(k_dec_rans_v2_lat_alpha, ntiles, 32, lat_smem(LUT_TWO_15), rb, LUT_TWO_15);
             else LAUNCH(k_dec_rans_v2_big<32>, (ntiles + 31) / 32, 32, 32 * 258 * 2 + 32 * 260, rb);
             AlphaArgs al{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->alpha.p, (uint8_t*)ctx->plane.p, (uint32_t*)ctx->rowcnt.p };
             LAUNCH(k_dec_alpha, ntiles, 256, 0, al);
@@ -650,25 +651,27 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
             // most 16 symbols (direct table, 64 KiB), 3..7 larger alphabets (two-level), 8..16 contexts, 17 grey plane
             RansV1LatArgs la{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 3, LUT_ONE_14 };
             FORK_SIDE(0); side_busy[0] = true;
-            LAUNCH(k_dec_rans_v1_lat, 3 * ntiles, 32, lat_smem(LUT_ONE_14), la);
+            auto k_dec_rans_v1_lat_values16 = k_dec_rans_v1_lat; auto k_dec_rans_v1_lat_values256 = k_dec_rans_v1_lat;
+            auto k_dec_rans_v1_lat_grey = k_dec_rans_v1_lat; auto k_dec_rans_v1_lat_ctx = k_dec_rans_v1_lat;   // names for the profile report
+            LAUNCH(k_dec_rans_v1_lat_values16, 3 * ntiles, 32, lat_smem(LUT_ONE_14), la);
             FORK_SIDE(1); side_busy[1] = true;
             la.j0 = 3; la.nj = 5; la.lut_bytes = LUT_TWO_14;
-            LAUNCH(k_dec_rans_v1_lat, 5 * ntiles, 32, lat_smem(LUT_TWO_14), la);
+            LAUNCH(k_dec_rans_v1_lat_values256, 5 * ntiles, 32, lat_smem(LUT_TWO_14), la);
             la.j0 = 17; la.nj = 1; la.lut_bytes = LUT_TWO_15;
-            LAUNCH(k_dec_rans_v1_lat, ntiles, 32, lat_smem(LUT_TWO_15), la);
+            LAUNCH(k_dec_rans_v1_lat_grey, ntiles, 32, lat_smem(LUT_TWO_15), la);
             BACK_TO_MAIN();
             la.j0 = 8; la.nj = 9; la.lut_bytes = LUT_TWO_14;   // context streams (two-level tables: they are short), then the walk
-            LAUNCH(k_dec_rans_v1_lat, 9 * ntiles, 32, lat_smem(LUT_TWO_14), la);
+            LAUNCH(k_dec_rans_v1_lat_ctx, 9 * ntiles, 32, lat_smem(LUT_TWO_14), la);
         } else {
         RansV1DecArgs rv{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 9, 0, 16 };
-        auto k8 = k_dec_rans_v1_small<8, 128>; auto k15 = k_dec_rans_v1_small<15, 128>; auto kbig = k_dec_rans_v1_big<32>;
-        LAUNCH(k8, (9 * ntiles + 127) / 128, 128, 0, rv);                     // contexts (9 symbols); grey tiles: nothing (N = 256)
+        auto k_dec_rans_v1_lane_8 = k_dec_rans_v1_small<8, 128>; auto k_dec_rans_v1_lane_15 = k_dec_rans_v1_small<15, 128>; auto k_dec_rans_v1_lane_big = k_dec_rans_v1_big<32>;
+        LAUNCH(k_dec_rans_v1_lane_8, (9 * ntiles + 127) / 128, 128, 0, rv);                     // contexts (9 symbols); grey tiles: nothing (N = 256)
         rv.c0 = 9; rv.nc = 8;
-        LAUNCH(k15, (8 * ntiles + 127) / 128, 128, 0, rv);                    // value alphabets of 8 / 16 symbols
+        LAUNCH(k_dec_rans_v1_lane_15, (8 * ntiles + 127) / 128, 128, 0, rv);                    // value alphabets of 8 / 16 symbols
         rv.nmin = 16; rv.nmax = 256;
-        LAUNCH(kbig, (8 * ntiles + 31) / 32, 32, 32 * 258 * 2 + 32 * 260, rv); // value alphabets of 32..256 symbols
+        LAUNCH(k_dec_rans_v1_lane_big, (8 * ntiles + 31) / 32, 32, 32 * 258 * 2 + 32 * 260, rv); // value alphabets of 32..256 symbols
         rv.c0 = 0; rv.nc = 1;
-        LAUNCH(kbig, (ntiles + 31) / 32, 32, 32 * 258 * 2 + 32 * 260, rv);     // grey planes
+        LAUNCH(k_dec_rans_v1_lane_big, (ntiles + 31) / 32, 32, 32 * 258 * 2 + 32 * 260, rv);     // grey planes
         }
     }
     if (any1 || any2) {
