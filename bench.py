@@ -48,7 +48,32 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
 
+    def _run_nvml(self):
+        """Fast path: NVML in-process (10 ms period); returns False when NVML is unavailable."""
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            bits = {"hw_slowdown": N.nvmlClocksEventReasonHwSlowdown if hasattr(N, "nvmlClocksEventReasonHwSlowdown") else 0x8,
+                    "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+        except Exception:
+            return False
+        while not self._stop_evt.is_set():
+            try:
+                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                r = int(get_reasons(h))
+                self.rows.append([str(self.index), str(sm), str(mx)] + ["Active" if r & bits[k] else "Not Active"
+                                                                         for k in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.01)
+        return True
+
     def run(self):
+        if self._run_nvml():
+            return
         while not self._stop_evt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],

@@ -263,6 +263,7 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     if (const char* e = getenv("XPNGB_LAT_MAX_BLOCKS")) ctx->lat_max_blocks = (uint32_t)atol(e);
     { auto p = k_rans_v2_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * PAIR_BLK * 24); }
     { auto p = k_rans_v1_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * PAIR_BLK * 24); }
+    cudaFuncSetAttribute(k_dec_unpredict_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, UNR_WARPS * 2 * 32 * UNR_PITCH);
     cudaFuncSetAttribute(k_dec_walk_smem<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WALK_SMEM_MAX_SYMS / 8 + 32) * 4);
     cudaFuncSetAttribute(k_dec_rans_v1_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, lat_smem(LUT_ONE_14));
     *out = ctx;
@@ -693,8 +694,11 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
         if (any1) LAUNCH(k_dec_residuals<1>, nseg, 256, 0, ch);
         if (any2) { LAUNCH(k_dec_residuals<2>, nseg, 256, 0, ch); LAUNCH(k_dec_residuals_grey, nseg, 256, 0, ch); }
         UnpredArgs ua{ d_tiles, d_imgs, d_dt, din, (const uint32_t*)ctx->resv.p, (const uint8_t*)ctx->plane.p, (const RowInfo*)ctx->rows.p,
-                       (uint4*)ctx->edge.p };
-        LAUNCH(k_dec_unpredict, ntiles, UNP_THREADS, 0, ua);
+                       (uint4*)ctx->edge.p, 0 };
+        uint32_t maxw = 0;
+        for (const TileDesc& t : P.tiles) if (t.w > maxw) maxw = t.w;
+        if (!getenv("XPNGB_UNPRED_OLD")) { LAUNCH(k_dec_unpredict_rows, ntiles, UNR_WARPS * 32, UNR_WARPS * 2 * 32 * UNR_PITCH, ua); ua.min_w = UNR_MAXW; }
+        if (ua.min_w == 0 || maxw > UNR_MAXW) LAUNCH(k_dec_unpredict, ntiles, UNP_THREADS, 0, ua);
         if (any2) LAUNCH(k_dec_grey_raw, ntiles, 256, 0, d_tiles, d_imgs, (const DecTile*)d_dt, din);
     }
     if (any7) LAUNCH(k_load7, dim3(296, n), 256, 0, (const ImageDesc*)ctx->imgs.p, (const uint64_t*)ctx->offs.p, din);   // stored images: flat copies

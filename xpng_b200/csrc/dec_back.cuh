@@ -409,6 +409,7 @@ struct UnpredArgs {
     const uint8_t* plane;     // alpha plane (RGBA)
     const RowInfo* rows;      // RGBA: first residual index of each row
     uint4* edge;              // strip hand-over scratch per tile row (tiles wider than UNP_THREADS)
+    uint32_t min_w;           // k_dec_unpredict only: skip tiles up to this width (they go to k_dec_unpredict_rows)
 };
 
 template <int PXSZ>
@@ -489,8 +490,200 @@ __global__ void __launch_bounds__(UNP_THREADS) k_dec_unpredict(UnpredArgs A) {
     if (mode == 7 || (mode & 0x100)) return;
     const DecTile* d = A.dt + tile;
     if (d->m == 0 || d->m == 0xFE || d->m == 0xFF || ((d->m >> 4) == 2 && (d->m & 8))) return;
+    if (t.w <= A.min_w) return;
     if (t.pxsz == 4) unpredict_tile<4>(A, t, d, slots);
     else unpredict_tile<3>(A, t, d, slots);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Un-predict, row-band pipeline (libxpng.c:811-814, :866-897, :911-914).
+// A pixel needs L, U, UL.  Lane r of a warp owns ROW y0 + r of a 32-row band and walks it left to
+// right one pixel per step, one step behind the lane above: at step s lane r is at x = s - r.  Then
+//   L  = the lane's own previous pixel (register),
+//   U  = the pixel lane r-1 produced in the previous step (one shfl_up),
+//   UL = the U of the lane's own previous step (register),
+// so a step is a shuffle plus ALU work: no block barrier and no shared-memory slots per step, and
+// every lane streams through its own row (sector-friendly loads, word-sized stores).  Bands are
+// pipelined over the warps of the CTA: warp b % NW owns band b, lane 0 takes U from the last row of
+// the band above, which that band's last lane leaves in a shared boundary row together with a
+// monotonic progress counter (published every 32 columns; the lower band waits on it).
+// ------------------------------------------------------------------------------------------------
+constexpr int UNR_WARPS = 16;
+constexpr int UNR_MAXW = 672;        // widest tile (666) rounded up
+constexpr int UNR_PITCH = 32 * 4 + 4;   // bytes per staged row chunk (32 pixels of up to 4 bytes, padded)
+
+// Output staging: a lane's pixels would be 32 scattered sub-word stores per step; instead each warp stages
+// two 32-column chunks of its band in shared memory and writes a finished chunk row by row (contiguous bytes).
+template <int PXSZ>
+__device__ __forceinline__ void unr_flush(const uint8_t* sb, uint8_t* dst, const TileDesc& t, uint32_t y0, uint32_t chunk, uint32_t lane) {
+    const uint32_t ncols = min(32u, t.w - 32u * chunk), nbytes = ncols * PXSZ;
+    const uint8_t* src = sb + (chunk & 1u) * (32 * UNR_PITCH);
+#pragma unroll 4
+    for (uint32_t r = 0; r < 32; r++) {
+        if (y0 + r >= t.h) break;
+        uint8_t* o = dst + (uint64_t)(y0 + r) * t.bpr + (uint64_t)PXSZ * 32u * chunk;
+        for (uint32_t k = lane; k < nbytes; k += 32) o[k] = src[r * UNR_PITCH + k];
+    }
+}
+
+// Byte-parallel arithmetic on the three colour channels packed in one word (0x00BBGGRR): every operation below is
+// exact modulo 256 per byte, which is all the reconstruction needs (libxpng.c:21, :27-30, :813).
+__device__ __forceinline__ uint32_t swar_add(uint32_t a, uint32_t b) {        // per-byte a + b (mod 256)
+    return ((a & 0x7F7F7F7Fu) + (b & 0x7F7F7F7Fu)) ^ ((a ^ b) & 0x80808080u);
+}
+__device__ __forceinline__ uint32_t swar_unzz(uint32_t u) {                   // per-byte (u >> 1) ^ -(u & 1)
+    return ((u >> 1) & 0x7F7F7F7Fu) ^ ((u & 0x01010101u) * 0xFFu);
+}
+__device__ __forceinline__ uint32_t swar_avg2(uint32_t l, uint32_t u) {       // per-byte (l + u + 1) >> 1
+    return (l | u) - (((l ^ u) >> 1) & 0x7F7F7F7Fu);
+}
+__device__ __forceinline__ uint32_t swar_grad3(uint32_t l, uint32_t u, uint32_t ul) {   // per-byte ((3l + 3u - 2ul + 2) >> 2) mod 256
+    // 16-bit lanes with a +512 bias keep every lane non-negative (range 4 .. 2044); 512 >> 2 = 128 is removed mod 256
+    const uint32_t l01 = (l & 0xFFu) | ((l & 0xFF00u) << 8), u01 = (u & 0xFFu) | ((u & 0xFF00u) << 8), q01 = (ul & 0xFFu) | ((ul & 0xFF00u) << 8);
+    const uint32_t l2 = (l >> 16) & 0xFFu, u2 = (u >> 16) & 0xFFu, q2 = (ul >> 16) & 0xFFu;
+    const uint32_t t01 = 3u * (l01 + u01) + 0x02020202u - 2u * q01;            // + 514 per lane = 2 + 512
+    const uint32_t t2 = 3u * (l2 + u2) + 514u - 2u * q2;
+    const uint32_t p01 = ((t01 >> 2) + 0x00800080u) & 0x00FF00FFu, p2 = ((t2 >> 2) + 128u) & 0xFFu;   // +128 == -128 (mod 256), no borrow
+    return (p01 & 0xFFu) | ((p01 >> 8) & 0xFF00u) | (p2 << 16);
+}
+
+// PM: interior predictor 0 left, 1 up, 2 avg2, 3 grad3; GSUB: residual green added back to red and blue.
+template <int PXSZ, int PM, bool GSUB>
+__device__ __forceinline__ void unpredict_rows(const UnpredArgs& A, const TileDesc& t, const DecTile* d, uint32_t (*brow)[UNR_MAXW],
+                                               volatile uint32_t* prog, uint8_t* stage) {
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint8_t* blob = A.in + d->blob_off;
+    const uint32_t* res = A.resv + t.px_off;
+    const uint8_t* pl = A.plane + t.px_off;
+    const RowInfo* rows = A.rows + t.row_off;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(t.src_off);
+    const bool grey = (d->m >> 4) == 2;
+    const uint32_t fp = ld32u(blob + 8);   // first pixel, MSB-first bits
+    uint32_t first;
+    if (grey) first = (fp >> 24) * 0x010101u;
+    else if (PXSZ == 4) first = ((fp >> 24) & 255u) | (((fp >> 16) & 255u) << 8) | (((fp >> 8) & 255u) << 16) | ((fp & 255u) << 24);
+    else first = ((fp >> 24) & 255u) | (((fp >> 16) & 255u) << 8) | (((fp >> 8) & 255u) << 16);
+    const uint32_t w = t.w, nbands = (t.h + 31) / 32;
+    const uint32_t stride = w + 1;                         // progress units per band: columns done (0..w)
+    uint8_t* sb = stage + wid * (2 * 32 * UNR_PITCH);
+    for (uint32_t b = wid, seq = 0; b < nbands; b += UNR_WARPS, seq++) {
+        const uint32_t y = b * 32 + lane;
+        const bool rowok = y < t.h;
+        const uint32_t lastlane = min(31u, t.h - 1 - b * 32);   // lane holding the band's last row
+        uint32_t* mybrow = brow[wid];
+        const uint32_t upidx = (wid + UNR_WARPS - 1) % UNR_WARPS;
+        const uint32_t* upbrow = brow[upidx];
+        const uint32_t upbase = (wid == 0 ? seq - 1 : seq) * stride;     // progress value of the band above when it has done 0 columns
+        uint32_t left = 0, uprev = 0, prevout = 0;           // L, previous U (= UL), my pixel of the previous step (handed down)
+        uint32_t idx = (PXSZ == 4 && rowok) ? rows[y].idx : 0u;
+        const uint8_t* prow = pl + (uint64_t)y * w;
+        const uint32_t* rrow = res + (uint64_t)y * w - 1;    // RGB: residual of (x, y) at rrow[x]
+        // RGB: the lane's residuals are consecutive words of its row; they are fetched RING steps ahead into a
+        // register ring (static indices: the step loop is unrolled by RING), so no load ever sits on the
+        // L -> pixel -> L chain.  RGBA residuals are indexed by the running count of coded pixels: one step ahead.
+        constexpr int RING = 8;
+        uint32_t rn[RING];
+        uint32_t rnext = 0, anext = 255;
+#pragma unroll
+        for (int k = 0; k < RING; k++) rn[k] = 0;
+        if (rowok) {
+            if (PXSZ == 3) {   // slot j is consumed at steps s == j (mod RING); the lane's column c is consumed at step c + lane
+#pragma unroll
+                for (int c = 0; c < RING; c++) {
+                    const uint32_t v = ((uint32_t)c < w && (y || c)) ? rrow[c] : 0u;
+                    const uint32_t slot = (lane + (uint32_t)c) % RING;
+#pragma unroll
+                    for (int k = 0; k < RING; k++) rn[k] = slot == (uint32_t)k ? v : rn[k];
+                }
+            } else { anext = prow[0]; rnext = res[idx]; }
+        }
+        const uint32_t steps = w + 31;
+        uint32_t flushed = 0;                                // chunks written out so far
+        for (uint32_t s0 = 0; s0 < steps; s0 += RING) {
+#pragma unroll
+            for (int j = 0; j < RING; j++) {
+                const uint32_t s = s0 + j;
+                if (s >= steps) break;
+                if (b && (s & 7u) == 0) {                    // lane 0 will need columns s .. s + 7 of the band above
+                    const uint32_t need = upbase + min(s + 8u, w);
+                    while (prog[upidx] < need) { }
+                    __syncwarp();
+                }
+                const uint32_t x = s - lane;
+                const bool act = rowok && s >= lane && x < w;
+                uint32_t U = __shfl_up_sync(0xffffffffu, prevout, 1);
+                if (lane == 0) U = (b && x < w) ? upbrow[x] : 0u;
+                uint32_t pix = 0;
+                const uint32_t rv3 = rn[j];                  // static ring index: slot j <-> steps s == j (mod RING)
+                if (act) {
+                    bool coded = !(x == 0 && y == 0);
+                    const uint32_t a = anext, rv = PXSZ == 3 ? rv3 : rnext;
+                    if (PXSZ == 4) {
+                        if (a == 0) coded = false;
+                        if (coded) idx++;
+                        if (x + 1 < w) anext = prow[x + 1];
+                        rnext = res[idx];                    // the slice has slack behind its last residual
+                    } else {
+                        rn[j] = __ldg(rrow + min(x + RING, w - 1));   // consumed RING steps from now (clamped: never a select on the loaded value)
+                    }
+                    // all three channels at once
+                    uint32_t r = swar_unzz(rv & 0x00FFFFFFu);
+                    if (GSUB && x && y) r = swar_add(r, ((r >> 8) & 0xFFu) * 0x00010001u);
+                    const uint32_t l3 = left & 0x00FFFFFFu, u3 = U & 0x00FFFFFFu, q3 = uprev & 0x00FFFFFFu;
+                    uint32_t pd = PM == 0 ? l3 : (PM == 1 ? u3 : (PM == 2 ? swar_avg2(l3, u3) : swar_grad3(l3, u3, q3)));
+                    pd = y == 0 ? l3 : (x == 0 ? u3 : pd);
+                    const uint32_t val = (swar_add(r, pd) & 0x00FFFFFFu) | (PXSZ == 4 ? (a << 24) : 0u);
+                    pix = (x == 0 && y == 0) ? first : (coded ? val : 0u);
+                    uint8_t* o = sb + ((x >> 5) & 1u) * (32 * UNR_PITCH) + lane * UNR_PITCH + PXSZ * (x & 31u);
+                    if (PXSZ == 4) *reinterpret_cast<uint32_t*>(o) = pix;
+                    else { o[0] = (uint8_t)pix; o[1] = (uint8_t)(pix >> 8); o[2] = (uint8_t)(pix >> 16); }
+                    left = pix;
+                    if (lane == lastlane) mybrow[x] = pix;
+                }
+                uprev = U;
+                prevout = pix;
+                if (lane == lastlane && act && ((x & 7u) == 7u || x == w - 1)) {   // publish progress of the band's last row
+                    __threadfence_block();
+                    prog[wid] = seq * stride + x + 1;
+                }
+                if (s >= 62 && ((s - 62) & 31u) == 0) {      // every lane has finished chunk (s - 62) / 32
+                    __syncwarp();
+                    unr_flush<PXSZ>(sb, dst, t, b * 32, flushed, lane);
+                    flushed++;
+                    __syncwarp();
+                }
+            }
+        }
+        __syncwarp();
+        for (; flushed * 32 < w; flushed++) unr_flush<PXSZ>(sb, dst, t, b * 32, flushed, lane);
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(UNR_WARPS * 32) k_dec_unpredict_rows(UnpredArgs A) {
+    extern __shared__ __align__(16) uint8_t unr_stage[];   // [UNR_WARPS][2][32][UNR_PITCH]
+    __shared__ uint32_t brow[UNR_WARPS][UNR_MAXW];
+    __shared__ uint32_t prog_s[UNR_WARPS];
+    const uint32_t tile = blockIdx.x;
+    const TileDesc t = A.tiles[tile];
+    const uint32_t mode = A.imgs[t.img].mode;
+    if (mode == 7 || (mode & 0x100)) return;
+    const DecTile* d = A.dt + tile;
+    if (d->m == 0 || d->m == 0xFE || d->m == 0xFF || ((d->m >> 4) == 2 && (d->m & 8))) return;
+    if (t.w > UNR_MAXW) return;                       // very wide, flat tiles (thin images): k_dec_unpredict
+    if (threadIdx.x < UNR_WARPS) prog_s[threadIdx.x] = 0;
+    __syncthreads();
+    // specialise the inner loop on the tile's predictor (grey tiles: m & 3; colour tiles: avg2 / grad3, optional G)
+    const bool grey = (d->m >> 4) == 2;
+    const uint32_t pm = grey ? (d->m & 3u) : (((d->m >> 1) & 1u) ? 3u : 2u);
+    const bool G = !grey && (d->m & 1u);
+    if (t.pxsz == 4) {
+        if (pm == 3) { if (G) unpredict_rows<4, 3, true>(A, t, d, brow, prog_s, unr_stage); else unpredict_rows<4, 3, false>(A, t, d, brow, prog_s, unr_stage); }
+        else { if (G) unpredict_rows<4, 2, true>(A, t, d, brow, prog_s, unr_stage); else unpredict_rows<4, 2, false>(A, t, d, brow, prog_s, unr_stage); }
+    } else if (pm == 3) { if (G) unpredict_rows<3, 3, true>(A, t, d, brow, prog_s, unr_stage); else unpredict_rows<3, 3, false>(A, t, d, brow, prog_s, unr_stage); }
+    else if (pm == 2) { if (G) unpredict_rows<3, 2, true>(A, t, d, brow, prog_s, unr_stage); else unpredict_rows<3, 2, false>(A, t, d, brow, prog_s, unr_stage); }
+    else if (pm == 1) unpredict_rows<3, 1, false>(A, t, d, brow, prog_s, unr_stage);
+    else unpredict_rows<3, 0, false>(A, t, d, brow, prog_s, unr_stage);
 }
 
 // Raw grey plane (level 2, m = 0x28, libxpng.c:875-879)
