@@ -26,8 +26,9 @@ struct PinBuf { void* p = nullptr; size_t cap = 0; };
 
 struct xpngb_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr, side[2] = { nullptr, nullptr }, cur = nullptr;   // main stream, two side streams for independent chains, stream of the next launch
-    cudaEvent_t ev_fork = nullptr, ev_join[2] = { nullptr, nullptr };
+    static constexpr int NSIDE = 4;
+    cudaStream_t stream = nullptr, side[NSIDE] = {}, cur = nullptr;   // main stream, side streams for independent chains, stream of the next launch
+    cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, pe0 = nullptr, pe1 = nullptr;
     int profile = 0;   // 1: per-kernel CUDA-event timing accumulated (serialises the launches); 2: also print to stderr
     struct ProfRow { const char* name; double ms; uint32_t count; };
@@ -73,7 +74,8 @@ struct xpngb_ctx {
 
 // Independent serial chains (e.g. the value-stream blocks of level 2 while the context streams are walked)
 // run on the side stream: FORK makes it wait for everything launched so far, JOIN makes the main stream wait for it.
-#define FORK_SIDE(k) do { CK(cudaEventRecord(ctx->ev_fork, ctx->stream)); CK(cudaStreamWaitEvent(ctx->side[k], ctx->ev_fork, 0)); ctx->cur = ctx->side[k]; } while (0)
+#define FORK_SIDE(k) FORK_FROM(ctx->stream, k)
+#define FORK_FROM(src, k) do { CK(cudaEventRecord(ctx->ev_fork, (src))); CK(cudaStreamWaitEvent(ctx->side[k], ctx->ev_fork, 0)); ctx->cur = ctx->side[k]; } while (0)
 #define BACK_TO_MAIN() do { ctx->cur = ctx->stream; } while (0)
 #define JOIN_SIDE(k) do { ctx->cur = ctx->stream; CK(cudaEventRecord(ctx->ev_join[k], ctx->side[k])); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0)); } while (0)
 
@@ -209,7 +211,7 @@ static int m2_encode_tiles(xpngb_ctx* ctx, const Plan& P, uint32_t ntiles, uint3
     LAUNCH(k_m2_grey_front, nseg, 256, 0, d_tiles, d_seg_tile, (const uint8_t*)ctx->tclass.p, (uint8_t*)ctx->streams.p, (uint32_t*)ctx->hist.p);
     RansV1Args ra{ d_tiles, (TileState*)ctx->state.p, (const uint32_t*)ctx->hist.p, (const uint8_t*)ctx->tclass.p,
                    (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->blocks.p, (uint32_t*)ctx->tabs.p, ntiles, 0, 17, 0, 0 };
-    if (17 * ntiles <= ctx->lat_max_blocks) {
+    if (17 * ntiles <= ctx->lat_max_blocks * 5 / 2) {   // level 2 crosses over later than level 1 (profiles/: ~600 vs ~380 frames of 1080p)
         auto k_rans_v1_pair_16 = k_rans_v1_pair<16>; auto k_rans_v1_pair_256 = k_rans_v1_pair<256>;
         FORK_SIDE(0);                                 // alphabets above 16 symbols and the grey candidates: side stream
         RansV1Args rb = ra; rb.c0 = 9; rb.nc = 8; rb.nmin = 16;
@@ -248,12 +250,11 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     xpngb_ctx* ctx = new xpngb_ctx();
     ctx->device = device;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->side[0], cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->side[1], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_join[0], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_join[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) { delete ctx; return 1; }
+    for (int k = 0; k < xpngb_ctx::NSIDE; k++)
+        if (cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return 1; }
     ctx->cur = ctx->stream;
     cudaEventCreate(&ctx->pe0); cudaEventCreate(&ctx->pe1);
     if (const char* e = getenv("XPNGB_PROFILE")) ctx->profile = atoi(e) ? 2 : 0;
@@ -273,7 +274,8 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
 extern "C" void xpngb_destroy(xpngb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream); cudaStreamSynchronize(ctx->side[0]); cudaStreamSynchronize(ctx->side[1]);
+    cudaStreamSynchronize(ctx->stream);
+    for (int k = 0; k < xpngb_ctx::NSIDE; k++) cudaStreamSynchronize(ctx->side[k]);
     DevBuf* all[] = { &ctx->pixels, &ctx->norm, &ctx->files, &ctx->arena, &ctx->tiles, &ctx->imgs, &ctx->seg_tile, &ctx->costs,
                       &ctx->hist, &ctx->seginfo, &ctx->place, &ctx->vplace, &ctx->vcnt, &ctx->sym_area, &ctx->bits_area, &ctx->alpha,
                       &ctx->streams, &ctx->blocks, &ctx->state, &ctx->outs, &ctx->flags, &ctx->skip, &ctx->dimgs, &ctx->dtiles,
@@ -283,8 +285,8 @@ extern "C" void xpngb_destroy(xpngb_ctx* ctx) {
     if (ctx->pin_a.p) cudaFreeHost(ctx->pin_a.p);
     if (ctx->pin_b.p) cudaFreeHost(ctx->pin_b.p);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
-    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join[0]); cudaEventDestroy(ctx->ev_join[1]); cudaEventDestroy(ctx->pe0); cudaEventDestroy(ctx->pe1);
-    cudaStreamDestroy(ctx->side[0]); cudaStreamDestroy(ctx->side[1]);
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->pe0); cudaEventDestroy(ctx->pe1);
+    for (int k = 0; k < xpngb_ctx::NSIDE; k++) { cudaEventDestroy(ctx->ev_join[k]); cudaStreamDestroy(ctx->side[k]); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -382,13 +384,19 @@ static int encode_chunk(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32_t n
         mode[i] = m; any1 |= m == 1; any2 |= m == 2;
     }
     if (any1 && any2) {
-        // level 2 with some images that keep alpha (coded at level 1, libxpng.c:755): encode each run of one family on its own
-        uint64_t base = out_base; uint32_t a = 0;
-        while (a < n) {
-            const bool fam1 = mode[a] == 1; uint32_t b = a;
-            while (b < n && (mode[b] == 1) == fam1) b++;
-            if (encode_chunk(ctx, fam1 ? 1 : 2, imgs + a, b - a, dpix, dout, base, out_cap, out_offsets + a, out_sizes + a, &base)) return 1;
-            a = b;
+        // level 2 with some images that keep alpha (coded at level 1, libxpng.c:755): the batch is regrouped into the two
+        // families and each family is encoded in ONE pass (files of a family are adjacent in the arena; the offset table,
+        // not the arena order, is the contract)
+        uint64_t base = out_base;
+        for (int fam = 0; fam < 2; fam++) {
+            std::vector<uint32_t> idx;
+            for (uint32_t i = 0; i < n; i++) if ((mode[i] == 1) == (fam == 0)) idx.push_back(i);
+            if (idx.empty()) continue;
+            std::vector<xpngb_image> sub(idx.size());
+            std::vector<uint64_t> so(idx.size()), ss(idx.size());
+            for (size_t k = 0; k < idx.size(); k++) sub[k] = imgs[idx[k]];
+            if (encode_chunk(ctx, fam == 0 ? 1 : 2, sub.data(), (uint32_t)idx.size(), dpix, dout, base, out_cap, so.data(), ss.data(), &base)) return 1;
+            for (size_t k = 0; k < idx.size(); k++) { imgs[idx[k]] = sub[k]; out_offsets[idx[k]] = so[k]; out_sizes[idx[k]] = ss[k]; }
         }
         *used = base;
         return 0;
@@ -430,8 +438,14 @@ static int encode_chunk(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32_t n
                        (const uint8_t*)ctx->alpha.p, (uint8_t*)ctx->blocks.p, ntiles, 0, 9 };
         if (9 * ntiles <= ctx->lat_max_blocks) {
             auto k_rans_v2_pair_16 = k_rans_v2_pair<16>; auto k_rans_v2_pair_256 = k_rans_v2_pair<256>;
+            if (P.any_rgba) {                          // the alpha blocks are independent of the context blocks: side stream
+                RansV2Args rb = ra; rb.c0 = 9; rb.nc = 1;
+                FORK_SIDE(0);
+                LAUNCH(k_rans_v2_pair_256, (ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, rb);
+                BACK_TO_MAIN();
+            }
             LAUNCH(k_rans_v2_pair_16, (9 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 17 * PAIR_BLK * 24, ra);
-            if (P.any_rgba) { ra.c0 = 9; ra.nc = 1; LAUNCH(k_rans_v2_pair_256, (ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, ra); }
+            if (P.any_rgba) JOIN_SIDE(0);
         } else {
         auto k_rans_v2_lane_9 = k_rans_v2<9, 128>; auto k_rans_v2_lane_256 = k_rans_v2<256, 32>;
         LAUNCH(k_rans_v2_lane_9, (9 * ntiles + 127) / 128, 128, 9 * 128 * 16, ra);
@@ -619,7 +633,7 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     const uint32_t nseg = (uint32_t)P.seg_tile.size();
     const uint32_t* d_seg_tile = (const uint32_t*)ctx->seg_tile.p;
-    bool side_busy[2] = { false, false };
+    bool side_busy[xpngb_ctx::NSIDE] = {};
     if (any1 || any2) {
         ENSURE(streams, P.str_total); ENSURE(nlseq, P.px_total); ENSURE(rows, P.row_total * sizeof(RowInfo));
         ENSURE(rowcnt, P.row_total * 4); ENSURE(edge, P.row_total * 16);
@@ -627,12 +641,28 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
         if (P.any_rgba) { ENSURE(alpha, P.px_total); ENSURE(plane, P.px_total); }
         LAUNCH(k_dec_tile_offsets, (n + 127) / 128, 128, 0, d_imgs, din, d_dt, n, d_err);
     }
+    // Stream plan of one decode call.  Main stream: the level-2 family (or the only family).  side[2]: the level-1 family
+    // when both are present in the batch (config 0: the corpus mixes RGB and RGBA files).  side[0], side[1]: level-2
+    // value streams.  side[3]: the alpha plane.  Each family's chain is parse -> context rANS -> context walk.
+    uint32_t maxpx = 0;
+    for (const TileDesc& t : P.tiles) if (t.npx > maxpx) maxpx = t.npx;
+    const uint32_t wsm = (maxpx / 8 + 32) * 4;          // nibble-packed streams of the largest tile + pad words
+    auto launch_walk = [&](uint32_t mode) -> int {
+        WalkArgs wa{ d_tiles, d_imgs, d_dt, (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->nlseq.p, ntiles, mode };
+        if (ntiles <= 592 && maxpx <= WALK_SMEM_MAX_SYMS) LAUNCH(k_dec_walk_smem<0>, ntiles, 32, wsm, wa);
+        else if (ntiles <= 592) LAUNCH(k_dec_walk_lat<1>, ntiles, 32, 0, wa);
+        else LAUNCH(k_dec_walk_lat<4>, (ntiles + 3) / 4, 128, 0, wa);
+        return 0;
+    };
     if (any1) {
+        const bool own_stream = any2;                   // level-1 family next to a level-2 family
+        cudaStream_t f1 = own_stream ? ctx->side[2] : ctx->stream;
+        if (own_stream) { FORK_SIDE(2); side_busy[2] = true; }
         LAUNCH(k_dec_parse_m1, (ntiles + 127) / 128, 128, 0, d_tiles, d_imgs, din, d_dt, ntiles, d_err);
         RansDecArgs ra{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, (uint8_t*)ctx->alpha.p, ntiles, 0, 9 };
         const bool lat = 9 * ntiles <= ctx->lat_max_blocks;
-        if (P.any_rgba) {                             // the alpha plane is independent of the context walk: side stream
-            FORK_SIDE(1); side_busy[1] = true;
+        if (P.any_rgba) {                             // the alpha plane is independent of the context walk
+            FORK_FROM(f1, 3); side_busy[3] = true;
             RansDecArgs rb = ra; rb.c0 = 9; rb.nc = 1;
             auto k_dec_rans_v2_lat_alpha = k_dec_rans_v2_lat;
             if (lat) LAUNCH(k_dec_rans_v2_lat_alpha, ntiles, 32, lat_smem(LUT_TWO_15), rb, LUT_TWO_15);
@@ -640,20 +670,22 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
             AlphaArgs al{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->alpha.p, (uint8_t*)ctx->plane.p, (uint32_t*)ctx->rowcnt.p };
             LAUNCH(k_dec_alpha, ntiles, 256, 0, al);
             LAUNCH(k_dec_rows_rgba, ntiles, 32, 0, d_tiles, d_imgs, (const DecTile*)d_dt, (const uint32_t*)ctx->rowcnt.p, (RowInfo*)ctx->rows.p);
-            BACK_TO_MAIN();
         }
+        ctx->cur = f1;
         if (lat) LAUNCH(k_dec_rans_v2_lat, 9 * ntiles, 32, lat_smem(LUT_ONE_12), ra, LUT_ONE_12);
         else LAUNCH(k_dec_rans_v2_small<128>, (9 * ntiles + 127) / 128, 128, 0, ra);
+        if (launch_walk(1)) return 1;
+        BACK_TO_MAIN();
     }
     if (any2) {
         LAUNCH(k_dec_parse_m2, (ntiles + 127) / 128, 128, 0, d_tiles, d_imgs, din, d_dt, ntiles, d_err);
-        if (17 * ntiles <= ctx->lat_max_blocks) {
+        if (17 * ntiles <= ctx->lat_max_blocks * 5 / 2) {
             // value streams on the side streams (joined before the residual kernels); LAT_M2_ORDER: 0..2 alphabets of at
             // most 16 symbols (direct table, 64 KiB), 3..7 larger alphabets (two-level), 8..16 contexts, 17 grey plane
             RansV1LatArgs la{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 3, LUT_ONE_14 };
-            FORK_SIDE(0); side_busy[0] = true;
             auto k_dec_rans_v1_lat_values16 = k_dec_rans_v1_lat; auto k_dec_rans_v1_lat_values256 = k_dec_rans_v1_lat;
             auto k_dec_rans_v1_lat_grey = k_dec_rans_v1_lat; auto k_dec_rans_v1_lat_ctx = k_dec_rans_v1_lat;   // names for the profile report
+            FORK_SIDE(0); side_busy[0] = true;
             LAUNCH(k_dec_rans_v1_lat_values16, 3 * ntiles, 32, lat_smem(LUT_ONE_14), la);
             FORK_SIDE(1); side_busy[1] = true;
             la.j0 = 3; la.nj = 5; la.lut_bytes = LUT_TWO_14;
@@ -674,23 +706,15 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
         rv.c0 = 0; rv.nc = 1;
         LAUNCH(k_dec_rans_v1_lane_big, (ntiles + 31) / 32, 32, 32 * 258 * 2 + 32 * 260, rv);     // grey planes
         }
+        if (launch_walk(2)) return 1;
     }
     if (any1 || any2) {
-        for (uint32_t mode = 1; mode <= 2; mode++) {
-            if (!(mode == 1 ? any1 : any2)) continue;
-            WalkArgs wa{ d_tiles, d_imgs, d_dt, (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->nlseq.p, ntiles, mode };
-            uint32_t maxpx = 0;
-            for (const TileDesc& t : P.tiles) if (t.npx > maxpx) maxpx = t.npx;
-            const uint32_t wsm = (maxpx / 8 + 32) * 4;          // nibble-packed streams of the largest tile + pad words
-            if (ntiles <= 592 && maxpx <= WALK_SMEM_MAX_SYMS) LAUNCH(k_dec_walk_smem<0>, ntiles, 32, wsm, wa);
-            else if (ntiles <= 592) LAUNCH(k_dec_walk_lat<1>, ntiles, 32, 0, wa);
-            else LAUNCH(k_dec_walk_lat<4>, (ntiles + 3) / 4, 128, 0, wa);
-        }
+        if (side_busy[2]) JOIN_SIDE(2);                   // the other family's nl sequences
         ChunkArgs ch{ d_tiles, d_seg_tile, d_imgs, d_dt, (const uint8_t*)ctx->nlseq.p, (const uint8_t*)ctx->streams.p, din,
                       (uint32_t*)ctx->ccnt.p, (uint32_t*)ctx->cbit.p, (uint32_t*)ctx->resv.p, ntiles, d_err };
         LAUNCH(k_dec_chunk_hist, nseg, 256, 0, ch);
         LAUNCH(k_dec_chunk_scan, (ntiles + 3) / 4, 128, 0, ch);
-        for (int k = 0; k < 2; k++) if (side_busy[k]) JOIN_SIDE(k);
+        for (int k = 0; k < xpngb_ctx::NSIDE; k++) if (k != 2 && side_busy[k]) JOIN_SIDE(k);
         if (any1) LAUNCH(k_dec_residuals<1>, nseg, 256, 0, ch);
         if (any2) { LAUNCH(k_dec_residuals<2>, nseg, 256, 0, ch); LAUNCH(k_dec_residuals_grey, nseg, 256, 0, ch); }
         UnpredArgs ua{ d_tiles, d_imgs, d_dt, din, (const uint32_t*)ctx->resv.p, (const uint8_t*)ctx->plane.p, (const RowInfo*)ctx->rows.p,
