@@ -1,0 +1,89 @@
+"""PNG <-> .7 converter (xpng_b200/bin/seven, host C on zlib; reference 7/seven.c on libpng).  PIL is the checker:
+the reference's tool is `png_image_finish_read` to RGB / RGBA followed by normalize_RGBA (7/seven.c:4-37, :39-65)."""
+import glob
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from conftest import ROOT
+from oracle import pyoracle as po
+
+SEVEN = os.path.join(ROOT, "xpng_b200", "bin", "seven")
+XPNG = os.path.join(ROOT, "xpng_b200", "bin", "xpng")
+
+
+def _expected(png_path):
+    ref = Image.open(png_path)
+    ref = ref.convert("RGBA" if (ref.mode in ("RGBA", "LA") or "transparency" in ref.info) else "RGB")
+    return po.normalize(np.ascontiguousarray(np.array(ref)))
+
+
+def _variants():
+    rng = np.random.default_rng(5)
+    rgb = rng.integers(0, 256, (41, 67, 3), dtype=np.uint8)
+    rgba = rng.integers(0, 256, (41, 67, 4), dtype=np.uint8)
+    opaque = rgba.copy(); opaque[..., 3] = 255
+    dirty = rgba.copy(); dirty[::3, ::2, 3] = 0
+    out = {"rgb": Image.fromarray(rgb), "rgba": Image.fromarray(rgba), "rgba_opaque": Image.fromarray(opaque),
+           "rgba_dirty": Image.fromarray(dirty), "grey8": Image.fromarray(rgb[..., 0]), "grey1": Image.fromarray(rgb[..., 0] > 99),
+           "grey_alpha": Image.fromarray(rgba[..., :2].copy(), "LA"), "palette": Image.fromarray(rgb).convert("P"),
+           "palette16": Image.fromarray(rgb).quantize(16), "palette2": Image.fromarray(rgb).quantize(2), "one_pixel": Image.fromarray(rgb[:1, :1])}
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(_variants()))
+def test_to_7_matches_pil(tmp_path, name):
+    im = _variants()[name]
+    png, seven = str(tmp_path / "a.png"), str(tmp_path / "a.7")
+    im.save(png, bits=4) if name == "palette16" else (im.save(png, bits=1) if name == "palette2" else im.save(png))
+    assert subprocess.run([SEVEN, "--to_7", png, seven]).returncode == 0
+    want = _expected(png)
+    got = po.read_7(seven)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    back = str(tmp_path / "b.png")
+    assert subprocess.run([SEVEN, "--to_png", seven, back]).returncode == 0
+    assert np.array_equal(np.array(Image.open(back)), got)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "crops", "*.png"))) +
+                         sorted(glob.glob(os.path.join(ROOT, "tests", "_corpus", "*.png"))), ids=os.path.basename)
+def test_reference_images(tmp_path, path):
+    seven = str(tmp_path / "a.7")
+    assert subprocess.run([SEVEN, "--to_7", path, seven]).returncode == 0
+    want = _expected(path)
+    got = po.read_7(seven)
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
+def test_rejections_and_usage(tmp_path):
+    a16 = (np.arange(40 * 30, dtype=np.uint16).reshape(30, 40) * 50)
+    p16 = str(tmp_path / "g16.png"); Image.fromarray(a16).save(p16)
+    assert subprocess.run([SEVEN, "--to_7", p16, str(tmp_path / "x.7")]).returncode == 1          # 7/seven.c:48
+    good = str(tmp_path / "ok.png"); Image.fromarray(np.zeros((9, 9, 3), np.uint8) + 7).save(good)
+    raw = bytearray(open(good, "rb").read()); raw[-20] ^= 0x55
+    bad = str(tmp_path / "bad.png"); open(bad, "wb").write(raw)
+    assert subprocess.run([SEVEN, "--to_7", bad, str(tmp_path / "y.7")]).returncode == 1          # CRC / stream error
+    assert subprocess.run([SEVEN, "--to_7", str(tmp_path / "missing.png"), str(tmp_path / "z.7")]).returncode == 1
+    r = subprocess.run([SEVEN], capture_output=True, text=True)
+    assert r.returncode == 1 and "--to_7" in r.stdout and "--to_png" in r.stdout                   # 7/seven.c:73-78
+
+
+@pytest.mark.gpu
+def test_exchange_path_end_to_end(tmp_path):
+    """test.rb of the reference, re-expressed: PNG -> .7 -> .xpng (levels 1, 2, 7) -> .7 (cmp) -> PNG."""
+    for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "crops", "*.png")))[:5]:
+        src = str(tmp_path / "src.7")
+        assert subprocess.run([SEVEN, "--to_7", path, src]).returncode == 0
+        px = po.read_7(src)
+        for lv in (1, 2, 7):
+            xp, back = str(tmp_path / "r.xpng"), str(tmp_path / "r.7")
+            assert subprocess.run([XPNG, f"-{lv}", src, xp], capture_output=True).returncode == 0
+            assert open(xp, "rb").read() == po.encode(lv, px)
+            assert subprocess.run([XPNG, "-d", xp, back], capture_output=True).returncode == 0
+            assert open(back, "rb").read() == open(src, "rb").read()                               # test.rb:32 `cmp`
+        png = str(tmp_path / "out.png")
+        assert subprocess.run([SEVEN, "--to_png", back, png]).returncode == 0
+        assert np.array_equal(np.array(Image.open(png)), px)
