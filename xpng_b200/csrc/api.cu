@@ -26,7 +26,7 @@ struct PinBuf { void* p = nullptr; size_t cap = 0; };
 
 struct xpngb_ctx {
     int device = 0;
-    static constexpr int NSIDE = 4;
+    static constexpr int NSIDE = 5;
     cudaStream_t stream = nullptr, side[NSIDE] = {}, cur = nullptr;   // main stream, side streams for independent chains, stream of the next launch
     cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, pe0 = nullptr, pe1 = nullptr;
@@ -682,9 +682,10 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
         if (17 * ntiles <= ctx->lat_max_blocks * 5 / 2) {
             // value streams on the side streams (joined before the residual kernels); LAT_M2_ORDER: 0..2 alphabets of at
             // most 16 symbols (direct table, 64 KiB), 3..7 larger alphabets (two-level), 8..16 contexts, 17 grey plane
-            RansV1LatArgs la{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 3, LUT_ONE_14 };
+            RansV1LatArgs la{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 3, LUT_ONE_14, 0u, ~0u };
             auto k_dec_rans_v1_lat_values16 = k_dec_rans_v1_lat; auto k_dec_rans_v1_lat_values256 = k_dec_rans_v1_lat;
             auto k_dec_rans_v1_lat_grey = k_dec_rans_v1_lat; auto k_dec_rans_v1_lat_ctx = k_dec_rans_v1_lat;   // names for the profile report
+            auto k_dec_rans_v1_lat_ctx_short = k_dec_rans_v1_lat;
             FORK_SIDE(0); side_busy[0] = true;
             LAUNCH(k_dec_rans_v1_lat_values16, 3 * ntiles, 32, lat_smem(LUT_ONE_14), la);
             FORK_SIDE(1); side_busy[1] = true;
@@ -693,8 +694,16 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
             la.j0 = 17; la.nj = 1; la.lut_bytes = LUT_TWO_15;
             LAUNCH(k_dec_rans_v1_lat_grey, ntiles, 32, lat_smem(LUT_TWO_15), la);
             BACK_TO_MAIN();
-            la.j0 = 8; la.nj = 9; la.lut_bytes = LUT_TWO_14;   // context streams (two-level tables: they are short), then the walk
-            LAUNCH(k_dec_rans_v1_lat_ctx, 9 * ntiles, 32, lat_smem(LUT_TWO_14), la);
+            // context streams: the few long ones (they bound the walk's start on real images) get the 64 KiB direct table,
+            // the many short ones a two-level table on a side stream, so that everything stays resident
+            constexpr uint32_t CTX_LONG = 24576;
+            la.j0 = 8; la.nj = 9; la.lut_bytes = LUT_TWO_14; la.n_lo = 0; la.n_hi = CTX_LONG;
+            FORK_SIDE(4); side_busy[4] = true;
+            LAUNCH(k_dec_rans_v1_lat_ctx_short, 9 * ntiles, 32, lat_smem(LUT_TWO_14), la);
+            BACK_TO_MAIN();
+            la.lut_bytes = LUT_ONE_14; la.n_lo = CTX_LONG; la.n_hi = ~0u;
+            LAUNCH(k_dec_rans_v1_lat_ctx, 9 * ntiles, 32, lat_smem(LUT_ONE_14), la);
+            JOIN_SIDE(4); side_busy[4] = false;           // the walk needs every context stream
         } else {
         RansV1DecArgs rv{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 9, 0, 16 };
         auto k_dec_rans_v1_lane_8 = k_dec_rans_v1_small<8, 128>; auto k_dec_rans_v1_lane_15 = k_dec_rans_v1_small<15, 128>; auto k_dec_rans_v1_lane_big = k_dec_rans_v1_big<32>;

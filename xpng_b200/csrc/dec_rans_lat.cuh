@@ -248,6 +248,7 @@ struct RansV1LatArgs {
     uint32_t ntiles;
     uint32_t j0, nj;        // range of LAT_M2_ORDER handled by this launch
     uint32_t lut_bytes;
+    uint32_t n_lo, n_hi;    // only blocks with n_lo <= symbols < n_hi (long and short blocks get differently sized tables)
 };
 
 __global__ void __launch_bounds__(32) k_dec_rans_v1_lat(RansV1LatArgs A) {
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(32) k_dec_rans_v1_lat(RansV1LatArgs A) {
     uint8_t* out = A.streams + t.str_off + b.soff;
     const uint32_t n = b.n;
     if (b.type == 0 || n == 0) return;
+    if (n < A.n_lo || n >= A.n_hi) return;
     const uint8_t* side = blob + 8; const uint8_t* side_end = blob + 4 + d->bsz;
     const uint32_t bitpos = d->bitpos[c];
     const bool ctx = !grey && c < 9;
