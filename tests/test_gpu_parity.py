@@ -218,3 +218,29 @@ def test_fuzzed_files_never_crash(codec):
             except RuntimeError:
                 pass
         assert np.array_equal(codec.decode([good])[0], po.normalize(img))
+
+
+def test_thin_tiles_first_in_batch(codec):
+    """Regression (found by tools/parity_sweep.py): a 1-pixel-wide tile whose scratch slice starts the buffer must not
+    read the word before its residual plane; thin and very wide tiles take different un-predict kernels."""
+    batch = [synth.rgb(1823, 1, 5), synth.rgb(1, 1399, 6), synth.rgb(196, 393, 7), synth.rgba(9, 914, 8), synth.rgb(436, 3, 9)]
+    for lv in (1, 2):
+        want = [po.encode(lv, im) for im in batch]
+        assert codec.encode(lv, batch) == want
+        for b, im in zip(codec.decode(want), batch):
+            assert np.array_equal(b, po.normalize(im))
+
+
+def test_randomised_sweep(codec):
+    """A slice of tools/parity_sweep.py (mixed batches of random shapes and content classes) on every run."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("parity_sweep", os.path.join(ROOT, "tools", "parity_sweep.py"))
+    ps = importlib.util.module_from_spec(spec); spec.loader.exec_module(ps)
+    rng = np.random.default_rng(31337)
+    for _ in range(20):
+        batch = [ps.make(rng, []) for _ in range(int(rng.integers(1, 6)))]
+        for lv in (1, 2, 7):
+            want = [po.encode(lv, im) for im in batch]
+            assert codec.encode(lv, batch) == want, [im.shape for im in batch]
+            for b, im in zip(codec.decode(want), batch):
+                assert np.array_equal(b, po.normalize(im)), im.shape

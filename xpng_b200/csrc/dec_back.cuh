@@ -624,7 +624,9 @@ __device__ __forceinline__ void unpredict_rows(const UnpredArgs& A, const TileDe
                         if (x + 1 < w) anext = prow[x + 1];
                         rnext = res[idx];                    // the slice has slack behind its last residual
                     } else {
-                        rn[j] = __ldg(rrow + min(x + RING, w - 1));   // consumed RING steps from now (clamped: never a select on the loaded value)
+                        // consumed RING steps from now; the index is clamped into the row (row 0 has no residual at x = 0:
+                        // rrow[0] would be the word before the tile's slice), so the loaded value never needs a select
+                        rn[j] = __ldg(rrow + max(min(x + RING, w - 1), y ? 0u : 1u));
                     }
                     // all three channels at once
                     uint32_t r = swar_unzz(rv & 0x00FFFFFFu);
