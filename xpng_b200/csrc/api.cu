@@ -264,7 +264,8 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     if (const char* e = getenv("XPNGB_LAT_MAX_BLOCKS")) ctx->lat_max_blocks = (uint32_t)atol(e);
     { auto p = k_rans_v2_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * PAIR_BLK * 24); }
     { auto p = k_rans_v1_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * PAIR_BLK * 24); }
-    cudaFuncSetAttribute(k_dec_unpredict_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, UNR_WARPS * 2 * 32 * UNR_PITCH);
+    cudaFuncSetAttribute(k_dec_unpredict_rows<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2 * 32 * UNR_PITCH);
+    cudaFuncSetAttribute(k_dec_unpredict_rows<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 32 * UNR_PITCH);
     cudaFuncSetAttribute(k_dec_walk_smem<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WALK_SMEM_MAX_SYMS / 8 + 32) * 4);
     cudaFuncSetAttribute(k_dec_rans_v1_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, lat_smem(LUT_ONE_14));
     *out = ctx;
@@ -649,7 +650,9 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
     const uint32_t wsm = (maxpx / 8 + 32) * 4;          // nibble-packed streams of the largest tile + pad words
     auto launch_walk = [&](uint32_t mode) -> int {
         WalkArgs wa{ d_tiles, d_imgs, d_dt, (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->nlseq.p, ntiles, mode };
-        if (ntiles <= 592 && maxpx <= WALK_SMEM_MAX_SYMS) LAUNCH(k_dec_walk_smem<0>, ntiles, 32, wsm, wa);
+        // the shared-memory walk only pays when every tile's CTA is resident at once (no waves): 227 KB per SM, 148 SMs
+        const uint32_t resident = 148u * ((227u * 1024u) / (wsm + 1024u));
+        if (ntiles <= resident && maxpx <= WALK_SMEM_MAX_SYMS) LAUNCH(k_dec_walk_smem<0>, ntiles, 32, wsm, wa);
         else if (ntiles <= 592) LAUNCH(k_dec_walk_lat<1>, ntiles, 32, 0, wa);
         else LAUNCH(k_dec_walk_lat<4>, (ntiles + 3) / 4, 128, 0, wa);
         return 0;
@@ -730,8 +733,11 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
                        (uint4*)ctx->edge.p, 0 };
         uint32_t maxw = 0;
         for (const TileDesc& t : P.tiles) if (t.w > maxw) maxw = t.w;
-        if (!getenv("XPNGB_UNPRED_OLD")) { LAUNCH(k_dec_unpredict_rows, ntiles, UNR_WARPS * 32, UNR_WARPS * 2 * 32 * UNR_PITCH, ua); ua.min_w = UNR_MAXW; }
-        if (ua.min_w == 0 || maxw > UNR_MAXW) LAUNCH(k_dec_unpredict, ntiles, UNP_THREADS, 0, ua);
+        // 16 warps per tile when tiles are fewer than SMs (shortest band pipeline), 8 otherwise (two CTAs per SM)
+        if (ntiles <= 148) LAUNCH(k_dec_unpredict_rows<16>, ntiles, 16 * 32, 16 * 2 * 32 * UNR_PITCH, ua);
+        else LAUNCH(k_dec_unpredict_rows<8>, ntiles, 8 * 32, 8 * 2 * 32 * UNR_PITCH, ua);
+        ua.min_w = UNR_MAXW;
+        if (maxw > UNR_MAXW) LAUNCH(k_dec_unpredict, ntiles, UNP_THREADS, 0, ua);   // very wide, flat tiles only
         if (any2) LAUNCH(k_dec_grey_raw, ntiles, 256, 0, d_tiles, d_imgs, (const DecTile*)d_dt, din);
     }
     if (any7) LAUNCH(k_load7, dim3(296, n), 256, 0, (const ImageDesc*)ctx->imgs.p, (const uint64_t*)ctx->offs.p, din);   // stored images: flat copies

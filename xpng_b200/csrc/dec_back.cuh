@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(UNP_THREADS) k_dec_unpredict(UnpredArgs A) {
 // the band above, which that band's last lane leaves in a shared boundary row together with a
 // monotonic progress counter (published every 32 columns; the lower band waits on it).
 // ------------------------------------------------------------------------------------------------
-constexpr int UNR_WARPS = 16;
+constexpr int UNR_WARPS = 16;       // warps per CTA of the single-frame variant; batches use 8 (two CTAs per SM)
 constexpr int UNR_MAXW = 672;        // widest tile (666) rounded up
 constexpr int UNR_PITCH = 32 * 4 + 4;   // bytes per staged row chunk (32 pixels of up to 4 bytes, padded)
 
@@ -548,7 +548,7 @@ __device__ __forceinline__ uint32_t swar_grad3(uint32_t l, uint32_t u, uint32_t 
 }
 
 // PM: interior predictor 0 left, 1 up, 2 avg2, 3 grad3; GSUB: residual green added back to red and blue.
-template <int PXSZ, int PM, bool GSUB>
+template <int PXSZ, int PM, bool GSUB, int NW>
 __device__ __forceinline__ void unpredict_rows(const UnpredArgs& A, const TileDesc& t, const DecTile* d, uint32_t (*brow)[UNR_MAXW],
                                                volatile uint32_t* prog, uint8_t* stage) {
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -566,12 +566,12 @@ __device__ __forceinline__ void unpredict_rows(const UnpredArgs& A, const TileDe
     const uint32_t w = t.w, nbands = (t.h + 31) / 32;
     const uint32_t stride = w + 1;                         // progress units per band: columns done (0..w)
     uint8_t* sb = stage + wid * (2 * 32 * UNR_PITCH);
-    for (uint32_t b = wid, seq = 0; b < nbands; b += UNR_WARPS, seq++) {
+    for (uint32_t b = wid, seq = 0; b < nbands; b += NW, seq++) {
         const uint32_t y = b * 32 + lane;
         const bool rowok = y < t.h;
         const uint32_t lastlane = min(31u, t.h - 1 - b * 32);   // lane holding the band's last row
         uint32_t* mybrow = brow[wid];
-        const uint32_t upidx = (wid + UNR_WARPS - 1) % UNR_WARPS;
+        const uint32_t upidx = (wid + NW - 1) % NW;
         const uint32_t* upbrow = brow[upidx];
         const uint32_t upbase = (wid == 0 ? seq - 1 : seq) * stride;     // progress value of the band above when it has done 0 columns
         uint32_t left = 0, uprev = 0, prevout = 0;           // L, previous U (= UL), my pixel of the previous step (handed down)
@@ -662,10 +662,11 @@ __device__ __forceinline__ void unpredict_rows(const UnpredArgs& A, const TileDe
     }
 }
 
-__global__ void __launch_bounds__(UNR_WARPS * 32) k_dec_unpredict_rows(UnpredArgs A) {
-    extern __shared__ __align__(16) uint8_t unr_stage[];   // [UNR_WARPS][2][32][UNR_PITCH]
-    __shared__ uint32_t brow[UNR_WARPS][UNR_MAXW];
-    __shared__ uint32_t prog_s[UNR_WARPS];
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) k_dec_unpredict_rows(UnpredArgs A) {
+    extern __shared__ __align__(16) uint8_t unr_stage[];   // [NW][2][32][UNR_PITCH]
+    __shared__ uint32_t brow[NW][UNR_MAXW];
+    __shared__ uint32_t prog_s[NW];
     const uint32_t tile = blockIdx.x;
     const TileDesc t = A.tiles[tile];
     const uint32_t mode = A.imgs[t.img].mode;
@@ -673,19 +674,19 @@ __global__ void __launch_bounds__(UNR_WARPS * 32) k_dec_unpredict_rows(UnpredArg
     const DecTile* d = A.dt + tile;
     if (d->m == 0 || d->m == 0xFE || d->m == 0xFF || ((d->m >> 4) == 2 && (d->m & 8))) return;
     if (t.w > UNR_MAXW) return;                       // very wide, flat tiles (thin images): k_dec_unpredict
-    if (threadIdx.x < UNR_WARPS) prog_s[threadIdx.x] = 0;
+    if (threadIdx.x < NW) prog_s[threadIdx.x] = 0;
     __syncthreads();
     // specialise the inner loop on the tile's predictor (grey tiles: m & 3; colour tiles: avg2 / grad3, optional G)
     const bool grey = (d->m >> 4) == 2;
     const uint32_t pm = grey ? (d->m & 3u) : (((d->m >> 1) & 1u) ? 3u : 2u);
     const bool G = !grey && (d->m & 1u);
     if (t.pxsz == 4) {
-        if (pm == 3) { if (G) unpredict_rows<4, 3, true>(A, t, d, brow, prog_s, unr_stage); else unpredict_rows<4, 3, false>(A, t, d, brow, prog_s, unr_stage); }
-        else { if (G) unpredict_rows<4, 2, true>(A, t, d, brow, prog_s, unr_stage); else unpredict_rows<4, 2, false>(A, t, d, brow, prog_s, unr_stage); }
-    } else if (pm == 3) { if (G) unpredict_rows<3, 3, true>(A, t, d, brow, prog_s, unr_stage); else unpredict_rows<3, 3, false>(A, t, d, brow, prog_s, unr_stage); }
-    else if (pm == 2) { if (G) unpredict_rows<3, 2, true>(A, t, d, brow, prog_s, unr_stage); else unpredict_rows<3, 2, false>(A, t, d, brow, prog_s, unr_stage); }
-    else if (pm == 1) unpredict_rows<3, 1, false>(A, t, d, brow, prog_s, unr_stage);
-    else unpredict_rows<3, 0, false>(A, t, d, brow, prog_s, unr_stage);
+        if (pm == 3) { if (G) unpredict_rows<4, 3, true, NW>(A, t, d, brow, prog_s, unr_stage); else unpredict_rows<4, 3, false, NW>(A, t, d, brow, prog_s, unr_stage); }
+        else { if (G) unpredict_rows<4, 2, true, NW>(A, t, d, brow, prog_s, unr_stage); else unpredict_rows<4, 2, false, NW>(A, t, d, brow, prog_s, unr_stage); }
+    } else if (pm == 3) { if (G) unpredict_rows<3, 3, true, NW>(A, t, d, brow, prog_s, unr_stage); else unpredict_rows<3, 3, false, NW>(A, t, d, brow, prog_s, unr_stage); }
+    else if (pm == 2) { if (G) unpredict_rows<3, 2, true, NW>(A, t, d, brow, prog_s, unr_stage); else unpredict_rows<3, 2, false, NW>(A, t, d, brow, prog_s, unr_stage); }
+    else if (pm == 1) unpredict_rows<3, 1, false, NW>(A, t, d, brow, prog_s, unr_stage);
+    else unpredict_rows<3, 0, false, NW>(A, t, d, brow, prog_s, unr_stage);
 }
 
 // Raw grey plane (level 2, m = 0x28, libxpng.c:875-879)
