@@ -58,6 +58,36 @@ def test_reference_images(tmp_path, path):
     assert got.shape == want.shape and np.array_equal(got, want)
 
 
+def _adam7_png(a):
+    """Hand-made Adam7 file (PIL cannot write interlaced PNGs): the seven passes, filter 0, one IDAT."""
+    import struct
+    import zlib
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+    h, w, c = a.shape
+    xs, ys, dx, dy = [0, 4, 0, 2, 0, 1, 0], [0, 0, 4, 0, 2, 0, 1], [8, 8, 4, 4, 2, 2, 1], [8, 8, 8, 4, 4, 2, 2]
+    raw = b""
+    for p in range(7):
+        sub = a[ys[p]::dy[p], xs[p]::dx[p]]
+        for row in sub if sub.size else []:
+            raw += b"\0" + row.tobytes()
+    return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, {3: 2, 4: 6}[c], 0, 0, 1)) +
+            chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b""))
+
+
+@pytest.mark.parametrize("shape", [(37, 53, 3), (1, 1, 3), (5, 3, 4), (64, 64, 4), (9, 2, 3)])
+def test_adam7_interlaced(tmp_path, shape):
+    a = np.random.default_rng(3).integers(0, 256, shape, dtype=np.uint8)
+    png, seven = str(tmp_path / "i.png"), str(tmp_path / "i.7")
+    open(png, "wb").write(_adam7_png(a))
+    assert np.array_equal(np.array(Image.open(png)), a)            # PIL agrees the file is a valid interlaced PNG
+    assert subprocess.run([SEVEN, "--to_7", png, seven]).returncode == 0
+    want = po.normalize(a)
+    got = po.read_7(seven)
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
 def test_rejections_and_usage(tmp_path):
     a16 = (np.arange(40 * 30, dtype=np.uint16).reshape(30, 40) * 50)
     p16 = str(tmp_path / "g16.png"); Image.fromarray(a16).save(p16)

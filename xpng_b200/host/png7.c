@@ -8,7 +8,7 @@
  *     produces for PNG_FORMAT_RGB / PNG_FORMAT_RGBA on sRGB-encoded files;
  *   - normalize_RGBA (7/seven.c:4-37): alpha == 0 pixels lose their colour, an all-opaque alpha plane is dropped;
  *   - store_7.
- * Not covered (returns 1): Adam7-interlaced files.  gAMA/iCCP are ignored (the corpus is sRGB, gAMA 0.45455).
+ * Adam7-interlaced files are de-interlaced pass by pass.  gAMA/iCCP are ignored (the corpus is sRGB, gAMA 0.45455).
  * --to_png writes filter-0 rows through zlib: valid PNG, pixel-identical, not byte-identical to libpng's file. */
 #include "seven.h"
 #include <stdio.h>
@@ -96,7 +96,7 @@ _Bool png_load(const char *fn, xpng_t *pm) {
     }
     if (!have_ihdr || !end || !w || !h || w > (1u << 24) || h > (1u << 24)) goto done;
     if (depth == 16) goto done;                                   /* 7/seven.c:48: linear formats are refused */
-    if (interlace) goto done;                                     /* Adam7: not implemented */
+    if (interlace > 1) goto done;
     u32_t ch;
     switch (ctype) {
         case 0: ch = 1; if (depth != 1 && depth != 2 && depth != 4 && depth != 8) goto done; break;
@@ -106,33 +106,27 @@ _Bool png_load(const char *fn, xpng_t *pm) {
         case 6: ch = 4; if (depth != 8) goto done; break;
         default: goto done;
     }
-    const u64_t rowb = ((u64_t)w * ch * depth + 7) / 8, bpp = (ch * depth + 7) / 8, rawsz = (rowb + 1) * h;
-    raw = malloc(rawsz);
+    /* passes: one for a progressive file, seven for Adam7 (PNG specification, section 8.2) */
+    static const u32_t XS[7] = { 0, 4, 0, 2, 0, 1, 0 }, YS[7] = { 0, 0, 4, 0, 2, 0, 1 }, DX[7] = { 8, 8, 4, 4, 2, 2, 1 }, DY[7] = { 8, 8, 8, 4, 4, 2, 2 };
+    const u32_t npass = interlace ? 7 : 1;
+    const u64_t bpp = (ch * depth + 7) / 8;
+    u64_t rawsz = 0;
+    for (u32_t ps = 0; ps < npass; ps++) {
+        const u64_t pw = interlace ? (w > XS[ps] ? (w - XS[ps] + DX[ps] - 1) / DX[ps] : 0) : w;
+        const u64_t ph = interlace ? (h > YS[ps] ? (h - YS[ps] + DY[ps] - 1) / DY[ps] : 0) : h;
+        if (pw && ph) rawsz += ph * (1 + (pw * ch * depth + 7) / 8);
+    }
+    raw = malloc(rawsz ? rawsz : 1);
     if (!raw) goto done;
     {
         z_stream z; memset(&z, 0, sizeof z);
         if (inflateInit(&z) != Z_OK) goto done;
         z.next_in = idat; z.avail_in = (uInt)idat_len; z.next_out = raw; z.avail_out = (uInt)rawsz;
-        /* streams beyond 4 GiB are outside what the .7 limits allow anyway (w, h <= 2^24 but s must fit memory) */
         const int rc = inflate(&z, Z_FINISH);
         const _Bool ok = (rc == Z_STREAM_END || rc == Z_OK || rc == Z_BUF_ERROR) && z.total_out == rawsz;
         inflateEnd(&z);
         if (!ok) goto done;
     }
-    /* un-filter in place (PNG specification, filter method 0) */
-    for (u64_t y = 0; y < h; y++) {
-        u8_t *row = raw + y * (rowb + 1) + 1;
-        const u8_t *up = y ? row - (rowb + 1) : NULL;
-        const u8_t ft = row[-1];
-        if (ft > 4) goto done;
-        for (u64_t i = 0; i < rowb; i++) {
-            const int a = i >= bpp ? row[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= bpp) ? up[i - bpp] : 0;
-            int pd = 0;
-            if (ft == 1) pd = a; else if (ft == 2) pd = b; else if (ft == 3) pd = (a + b) >> 1; else if (ft == 4) pd = paeth(a, b, c);
-            row[i] = (u8_t)(row[i] + pd);
-        }
-    }
-    /* expand to RGB / RGBA */
     const _Bool alpha = ctype == 4 || ctype == 6 || have_trns;
     const u32_t oc = alpha ? 4 : 3;
     out = malloc((u64_t)w * h * oc);
@@ -141,25 +135,45 @@ _Bool png_load(const char *fn, xpng_t *pm) {
     const u32_t key_g = ntrns >= 2 ? (((u32_t)trns[0] << 8) | trns[1]) : 0xFFFFFFFFu;
     const u32_t key_r = ntrns >= 6 ? (((u32_t)trns[0] << 8) | trns[1]) : 0xFFFFFFFFu, key_gg = ntrns >= 6 ? (((u32_t)trns[2] << 8) | trns[3]) : 0,
                 key_b = ntrns >= 6 ? (((u32_t)trns[4] << 8) | trns[5]) : 0;
-    for (u64_t y = 0; y < h; y++) {
-        const u8_t *row = raw + y * (rowb + 1) + 1;
-        u8_t *o = out + y * w * oc;
-        for (u64_t x = 0; x < w; x++, o += oc) {
-            u32_t r, g, b, a = 255;
-            if (ctype == 0 || ctype == 3) {
-                u32_t v;
-                if (depth == 8) v = row[x];
-                else { const u32_t per = 8 / depth, sh = (per - 1 - (u32_t)(x % per)) * depth; v = (row[x / per] >> sh) & maxv; }
-                if (ctype == 0) { if (have_trns && v == key_g) a = 0; r = g = b = v * 255u / maxv; }
-                else { if (v >= npal) goto done; r = pal[3 * v]; g = pal[3 * v + 1]; b = pal[3 * v + 2]; a = trns[v]; }
-            } else if (ctype == 2) {
-                r = row[3 * x]; g = row[3 * x + 1]; b = row[3 * x + 2];
-                if (have_trns && r == key_r && g == key_gg && b == key_b) a = 0;
-            } else if (ctype == 4) { r = g = b = row[2 * x]; a = row[2 * x + 1]; }
-            else { r = row[4 * x]; g = row[4 * x + 1]; b = row[4 * x + 2]; a = row[4 * x + 3]; }
-            o[0] = (u8_t)r; o[1] = (u8_t)g; o[2] = (u8_t)b;
-            if (alpha) o[3] = (u8_t)a;
+    u8_t *pass_base = raw;
+    for (u32_t ps = 0; ps < npass; ps++) {
+        const u64_t pw = interlace ? (w > XS[ps] ? (w - XS[ps] + DX[ps] - 1) / DX[ps] : 0) : w;
+        const u64_t ph = interlace ? (h > YS[ps] ? (h - YS[ps] + DY[ps] - 1) / DY[ps] : 0) : h;
+        if (!pw || !ph) continue;
+        const u64_t rowb = (pw * ch * depth + 7) / 8;
+        const u32_t xs = interlace ? XS[ps] : 0, ys = interlace ? YS[ps] : 0, dx = interlace ? DX[ps] : 1, dy = interlace ? DY[ps] : 1;
+        for (u64_t y = 0; y < ph; y++) {
+            /* un-filter in place (PNG specification, filter method 0) */
+            u8_t *row = pass_base + y * (rowb + 1) + 1;
+            const u8_t *up = y ? row - (rowb + 1) : NULL;
+            const u8_t ft = row[-1];
+            if (ft > 4) goto done;
+            for (u64_t i = 0; i < rowb; i++) {
+                const int a = i >= bpp ? row[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= bpp) ? up[i - bpp] : 0;
+                int pd = 0;
+                if (ft == 1) pd = a; else if (ft == 2) pd = b; else if (ft == 3) pd = (a + b) >> 1; else if (ft == 4) pd = paeth(a, b, c);
+                row[i] = (u8_t)(row[i] + pd);
+            }
+            /* expand to RGB / RGBA at the pass's positions */
+            for (u64_t x = 0; x < pw; x++) {
+                u8_t *o = out + ((u64_t)(ys + y * dy) * w + (xs + x * dx)) * oc;
+                u32_t r, g, b, a = 255;
+                if (ctype == 0 || ctype == 3) {
+                    u32_t v;
+                    if (depth == 8) v = row[x];
+                    else { const u32_t per = 8 / depth, sh = (per - 1 - (u32_t)(x % per)) * depth; v = (row[x / per] >> sh) & maxv; }
+                    if (ctype == 0) { if (have_trns && v == key_g) a = 0; r = g = b = v * 255u / maxv; }
+                    else { if (v >= npal) goto done; r = pal[3 * v]; g = pal[3 * v + 1]; b = pal[3 * v + 2]; a = trns[v]; }
+                } else if (ctype == 2) {
+                    r = row[3 * x]; g = row[3 * x + 1]; b = row[3 * x + 2];
+                    if (have_trns && r == key_r && g == key_gg && b == key_b) a = 0;
+                } else if (ctype == 4) { r = g = b = row[2 * x]; a = row[2 * x + 1]; }
+                else { r = row[4 * x]; g = row[4 * x + 1]; b = row[4 * x + 2]; a = row[4 * x + 3]; }
+                o[0] = (u8_t)r; o[1] = (u8_t)g; o[2] = (u8_t)b;
+                if (alpha) o[3] = (u8_t)a;
+            }
         }
+        pass_base += ph * (rowb + 1);
     }
     pm->p = out; out = NULL; pm->w = w; pm->h = h; pm->A = alpha; pm->s = (u64_t)w * h * oc;
     bad = 0;
