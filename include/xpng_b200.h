@@ -61,6 +61,24 @@ int xpngb_decode(xpngb_ctx *ctx, xpngb_image *imgs, uint32_t n,
                  const uint64_t *file_offsets, const uint64_t *file_sizes,
                  void *pixels, uint64_t pixels_cap, int pixels_on_device);
 
+/* Traversal-order operations of the exchange scheme (Mirroring_and_Rotating/tool.c:3-127; op codes in the order of
+ * its option table, tool.c:133).  TL and TR are empty functions in the reference and therefore plain copies. */
+enum { XPNGB_OP_R90 = 0, XPNGB_OP_R270 = 1, XPNGB_OP_MV = 2, XPNGB_OP_MH = 3, XPNGB_OP_MVH = 4, XPNGB_OP_TL = 5, XPNGB_OP_TR = 6 };
+
+/* Apply `op` to n pixmaps: image i is read at src + imgs[i].offset and written at dst + imgs[i].offset (same byte
+ * count, so the same offsets serve both buffers; src and dst must not overlap).  imgs[i].w and .h are swapped for the
+ * quarter turns.  Replaces op_mv/op_mh/op_mvh/op_r90/op_r270 (tool.c:3-119). */
+int xpngb_transform(xpngb_ctx *ctx, int op, xpngb_image *imgs, uint32_t n,
+                    const void *src, uint64_t size, int src_on_device, void *dst, int dst_on_device);
+
+/* xpngb_encode of the images as `op` would leave them — the "change the traversal order instead of transforming the
+ * pixmap" idea of Mirroring_and_Rotating/README.md:1-4: the files are byte-identical to `tool --op` followed by
+ * `xpng -level`, the caller's pixels are not touched, imgs[i].w/.h report the encoded orientation. */
+int xpngb_encode_oriented(xpngb_ctx *ctx, int level, int op, xpngb_image *imgs, uint32_t n,
+                          const void *pixels, uint64_t pixels_size, int pixels_on_device,
+                          void *out, uint64_t out_cap, int out_on_device,
+                          uint64_t *out_offsets, uint64_t *out_sizes);
+
 /* Device time of the kernels of the last encode/decode call on this context, in milliseconds
  * (CUDA events on the context's stream; excludes host<->device copies). */
 float xpngb_last_kernel_ms(const xpngb_ctx *ctx);

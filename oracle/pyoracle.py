@@ -179,3 +179,35 @@ def ref_decode(data, cli=REF_CLI):
         if r.returncode != 0:
             return None
         return read_7(dst)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Traversal-order operations (Mirroring_and_Rotating/tool.c) restated in numpy; test infrastructure like the rest.
+REF_TOOL = os.path.join(_REF_DIR, "tool")
+TOOL_OPS = ("r90", "r270", "mv", "mh", "mvh", "tl", "tr")          # option table, tool.c:133
+
+
+def orient(op, px):
+    """What `tool --<op>` leaves in the .7 file for pixmap px (h,w,c)."""
+    if op == "mv":       # op_mv, tool.c:3-26: rows swapped top <-> bottom
+        return px[::-1].copy()
+    if op == "mh":       # op_mh, tool.c:28-59: pixels of every row reversed
+        return px[:, ::-1].copy()
+    if op == "mvh":      # op_mvh, tool.c:61-90: both (a half turn)
+        return px[::-1, ::-1].copy()
+    if op == "r90":      # op_r90, tool.c:92-112: src(i,j) -> dst(j, h-1-i), a clockwise quarter turn
+        return np.ascontiguousarray(np.rot90(px, k=-1))
+    if op == "r270":     # op_r270, tool.c:114-119: op_mvh then op_r90
+        return np.ascontiguousarray(np.rot90(px[::-1, ::-1], k=-1))
+    if op in ("tl", "tr"):   # op_tl / op_tr, tool.c:121-127: empty bodies
+        return px.copy()
+    raise ValueError(op)
+
+
+def ref_orient(op, px):
+    """The unmodified reference tool on a .7 file (oracle/_ref/tool)."""
+    with tempfile.TemporaryDirectory(dir=_tmpdir()) as d:
+        a, b = os.path.join(d, "s.7"), os.path.join(d, "x.7")
+        write_7(a, px)
+        subprocess.run([REF_TOOL, "--" + op, a, b], check=True, stdout=subprocess.DEVNULL)
+        return read_7(b)

@@ -19,14 +19,14 @@ def declared_symbols():
     for h in ("xpng_b200.h", "xpng.h", "seven.h", "png7.h"):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-        names |= set(re.findall(r"\b((?:xpngb?_|store_7|load_7|png_load|png_store|seven_main)\w*)\s*\(", src))
+        names |= set(re.findall(r"\b((?:xpngb?_|store_7|load_7|png_load|png_store|ppm_load|ppm_store|seven_main)\w*)\s*\(", src))
     return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():
     L = xpng_b200.lib()
     syms = declared_symbols()
-    assert len(syms) >= 21
+    assert len(syms) >= 25
     for s in syms:
         assert hasattr(L, s), s
 

@@ -117,3 +117,37 @@ def test_exchange_path_end_to_end(tmp_path):
         png = str(tmp_path / "out.png")
         assert subprocess.run([SEVEN, "--to_png", back, png]).returncode == 0
         assert np.array_equal(np.array(Image.open(png)), px)
+
+
+# ---------------------------------------------------------------- P6 front end (ancestor/gray.c:667-682)
+
+def test_ppm_round_trip_and_header(tmp_path):
+    rgb = np.random.default_rng(9).integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    ppm, seven, back = str(tmp_path / "a.ppm"), str(tmp_path / "a.7"), str(tmp_path / "b.ppm")
+    Image.fromarray(rgb).save(ppm)                                  # PIL writes "P6\n53 37\n255\n"
+    assert subprocess.run([SEVEN, "--to_7", ppm, seven]).returncode == 0
+    assert np.array_equal(po.read_7(seven), rgb)
+    assert subprocess.run([SEVEN, "--to_ppm", seven, back]).returncode == 0
+    raw = open(back, "rb").read()
+    assert raw == b"P6\n53 37\n255\n" + rgb.tobytes()              # the header line of ancestor/gray.c:680
+    assert np.array_equal(np.array(Image.open(back)), rgb)
+
+
+def test_ppm_header_forms_and_rejections(tmp_path):
+    rgb = np.random.default_rng(10).integers(0, 256, (3, 5, 3), dtype=np.uint8)
+    seven = str(tmp_path / "a.7")
+    good = [b"P6 5 3 255\n", b"P6\n# made by hand\n5\t3\n# another\n255\n", b"P6\r\n5 3\r\n255 "]
+    for i, hdr in enumerate(good):
+        p = tmp_path / ("g%d.ppm" % i)
+        p.write_bytes(hdr + rgb.tobytes())
+        assert subprocess.run([SEVEN, "--to_7", str(p), seven]).returncode == 0, hdr
+        assert np.array_equal(po.read_7(seven), rgb), hdr
+    bad = [b"P6\n5 3\n65535\n" + bytes(90), b"P6\n5 3\n255\n" + rgb.tobytes()[:-1], b"P6\n0 3\n255\n", b"P6\n5 3\n", b"P6\n5 x\n255\n" + rgb.tobytes(),
+           b"P5\n5 3\n255\n" + rgb.tobytes(), b"P6\n5 3\n255" + rgb.tobytes()]
+    for i, data in enumerate(bad):
+        p = tmp_path / ("b%d.ppm" % i)
+        p.write_bytes(data)
+        assert subprocess.run([SEVEN, "--to_7", str(p), seven]).returncode == 1, data[:16]
+    # P6 has no alpha channel: an RGBA .7 is refused
+    po.write_7(seven, np.random.default_rng(1).integers(0, 256, (4, 4, 4), dtype=np.uint8))
+    assert subprocess.run([SEVEN, "--to_ppm", seven, str(tmp_path / "x.ppm")]).returncode == 1

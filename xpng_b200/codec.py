@@ -48,6 +48,11 @@ def lib():
         L.xpngb_encode.restype = C.c_int
         L.xpngb_encode.argtypes = [vp, C.c_int, C.POINTER(_Image), u32, vp, u64, C.c_int, vp, u64, C.c_int,
                                    C.POINTER(u64), C.POINTER(u64)]
+        L.xpngb_transform.restype = C.c_int
+        L.xpngb_transform.argtypes = [vp, C.c_int, C.POINTER(_Image), u32, vp, u64, C.c_int, vp, C.c_int]
+        L.xpngb_encode_oriented.restype = C.c_int
+        L.xpngb_encode_oriented.argtypes = [vp, C.c_int, C.c_int, C.POINTER(_Image), u32, vp, u64, C.c_int, vp, u64, C.c_int,
+                                            C.POINTER(u64), C.POINTER(u64)]
         L.xpngb_peek.restype = C.c_int; L.xpngb_peek.argtypes = [vp, u64, C.POINTER(_Image)]
         L.xpngb_decode.restype = C.c_int
         L.xpngb_decode.argtypes = [vp, C.POINTER(_Image), u32, vp, u64, C.c_int, C.POINTER(u64), C.POINTER(u64), vp, u64, C.c_int]
@@ -69,6 +74,9 @@ def lib():
         L.load_7.argtypes = [C.c_char_p, C.POINTER(_Xpng)]
         _lib = L
     return _lib
+
+
+OPS = {"r90": 0, "r270": 1, "mv": 2, "mh": 3, "mvh": 4, "tl": 5, "tr": 6}   # include/xpng_b200.h, order of tool.c:133
 
 
 def _align16(v):
@@ -183,6 +191,35 @@ class Codec:
             c = 3 + d.A
             out.append(px[d.offset: d.offset + d.w * d.h * c].reshape(d.h, d.w, c).copy())
         return out
+
+    # ---------------------------------------------------------------- traversal-order operations (Mirroring_and_Rotating/tool.c)
+    def _pack(self, images):
+        images = [np.ascontiguousarray(a, dtype=np.uint8) for a in images]
+        descs, total = self.layout([a.shape for a in images])
+        buf = np.zeros(total + 16, dtype=np.uint8)
+        for d, a in zip(descs, images):
+            buf[d.offset: d.offset + a.size] = a.reshape(-1)
+        return images, descs, total, buf
+
+    def transform(self, op, images):
+        """Apply op ('r90', 'r270', 'mv', 'mh', 'mvh', 'tl', 'tr' — tool.c:133) to a list of (h,w,3|4) arrays."""
+        images, descs, total, buf = self._pack(images)
+        out = np.empty(total + 16, dtype=np.uint8)
+        if lib().xpngb_transform(self._h, OPS[op], descs, len(images), buf.ctypes.data, total, 0, out.ctypes.data, 0):
+            raise RuntimeError("xpngb_transform: " + self._err())
+        return [out[d.offset: d.offset + d.w * d.h * (3 + d.A)].reshape(d.h, d.w, 3 + d.A).copy() for d in descs]
+
+    def encode_oriented(self, level, op, images):
+        """.xpng files of the images as `op` would leave them (tool --op followed by xpng -level), pixels untouched."""
+        images, descs, total, buf = self._pack(images)
+        n = len(images)
+        cap = int(lib().xpngb_encode_bound(descs, n))
+        out = np.empty(cap + 16, dtype=np.uint8)
+        offs, sizes = (C.c_uint64 * n)(), (C.c_uint64 * n)()
+        if lib().xpngb_encode_oriented(self._h, int(level), OPS[op], descs, n, buf.ctypes.data, total, 0, out.ctypes.data, cap, 0,
+                                       offs, sizes):
+            raise RuntimeError("xpngb_encode_oriented: " + self._err())
+        return [out[offs[i]: offs[i] + sizes[i]].tobytes() for i in range(n)]
 
     def ycocg_forward(self, rgb):
         rgb = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3)

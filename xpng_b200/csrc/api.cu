@@ -18,6 +18,7 @@
 #include "dec_back.cuh"
 #include "dec_rans_lat.cuh"
 #include "misc.cuh"
+#include "orient.cuh"
 
 using namespace xpb;
 
@@ -41,8 +42,8 @@ struct xpngb_ctx {
     // device scratch
     DevBuf pixels, norm, files, arena, tiles, imgs, seg_tile, costs, hist, seginfo, place, vplace, vcnt, sym_area,
         bits_area, alpha, streams, blocks, state, outs, flags, skip, dimgs, dtiles, plane, nlseq, rowcnt, rowbits,
-        rows, edge, errflag, hdr, offs, m2a, m2b, tclass, tabs, ccnt, cbit, resv;
-    PinBuf pin_a, pin_b;
+        rows, edge, errflag, hdr, offs, m2a, m2b, tclass, tabs, ccnt, cbit, resv, oriented, odesc;
+    PinBuf pin_a, pin_b, pin_o;   // pin_o: orientation descriptors (their upload may still be in flight when an encode reuses pin_a)
 };
 
 #define CK(call)                                                                                   \
@@ -281,10 +282,11 @@ extern "C" void xpngb_destroy(xpngb_ctx* ctx) {
                       &ctx->hist, &ctx->seginfo, &ctx->place, &ctx->vplace, &ctx->vcnt, &ctx->sym_area, &ctx->bits_area, &ctx->alpha,
                       &ctx->streams, &ctx->blocks, &ctx->state, &ctx->outs, &ctx->flags, &ctx->skip, &ctx->dimgs, &ctx->dtiles,
                       &ctx->plane, &ctx->nlseq, &ctx->rowcnt, &ctx->rowbits, &ctx->rows, &ctx->edge, &ctx->errflag, &ctx->hdr,
-                      &ctx->offs, &ctx->m2a, &ctx->m2b, &ctx->tclass, &ctx->tabs, &ctx->ccnt, &ctx->cbit, &ctx->resv };
+                      &ctx->offs, &ctx->m2a, &ctx->m2b, &ctx->tclass, &ctx->tabs, &ctx->ccnt, &ctx->cbit, &ctx->resv, &ctx->oriented, &ctx->odesc };
     for (DevBuf* b : all) if (b->p) cudaFree(b->p);
     if (ctx->pin_a.p) cudaFreeHost(ctx->pin_a.p);
     if (ctx->pin_b.p) cudaFreeHost(ctx->pin_b.p);
+    if (ctx->pin_o.p) cudaFreeHost(ctx->pin_o.p);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->pe0); cudaEventDestroy(ctx->pe1);
     for (int k = 0; k < xpngb_ctx::NSIDE; k++) { cudaEventDestroy(ctx->ev_join[k]); cudaStreamDestroy(ctx->side[k]); }
@@ -549,6 +551,90 @@ extern "C" int xpngb_encode(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Traversal-order operations (Mirroring_and_Rotating/tool.c): mirror / quarter-turn n pixmaps
+// ------------------------------------------------------------------------------------------------
+static int orient_launch(xpngb_ctx* ctx, int op, xpngb_image* imgs, uint32_t n, const uint8_t* dsrc, uint8_t* ddst) {
+    std::vector<OrientDesc> D(n);
+    uint64_t ctas = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        OrientDesc& d = D[i];
+        d.src = (uint64_t)(dsrc + imgs[i].offset); d.dst = (uint64_t)(ddst + imgs[i].offset);
+        d.w = (uint32_t)imgs[i].w; d.h = (uint32_t)imgs[i].h; d.pxsz = imgs[i].A ? 4 : 3; d.op = (uint32_t)op;
+        d.tiles_x = (d.w + ORI_T - 1) / ORI_T; d.first_cta = (uint32_t)ctas;
+        ctas += (uint64_t)d.tiles_x * ((d.h + ORI_T - 1) / ORI_T);
+        if (ctas > 0x7FFFFFFFull) FAIL("too many pixels for one orientation launch");
+    }
+    const size_t nb = n * sizeof(OrientDesc);
+    ENSURE(odesc, nb);
+    if (ensure_pin(ctx, ctx->pin_o, nb)) return 1;
+    memcpy(ctx->pin_o.p, D.data(), nb);
+    CK(cudaMemcpyAsync(ctx->odesc.p, ctx->pin_o.p, nb, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(k_orient, (unsigned)ctas, 256, 0, (const OrientDesc*)ctx->odesc.p, n);
+    if (op == OP_R90 || op == OP_R270) for (uint32_t i = 0; i < n; i++) { const uint64_t t = imgs[i].w; imgs[i].w = imgs[i].h; imgs[i].h = t; }
+    return 0;
+}
+
+static int orient_check(xpngb_ctx* ctx, int op, const xpngb_image* imgs, uint32_t n, uint64_t size) {
+    if (op < OP_R90 || op > OP_TR) FAIL("unknown orientation op %d", op);
+    for (uint32_t i = 0; i < n; i++) {
+        const xpngb_image& m = imgs[i];
+        if (!m.w || !m.h || m.w > (1u << 24) || m.h > (1u << 24)) FAIL("image %u: bad dimensions", i);
+        if (m.offset & 15) FAIL("image %u: pixel offset must be a multiple of 16", i);
+        if (m.offset + m.w * m.h * (3 + (m.A ? 1 : 0)) > size) FAIL("image %u: pixels exceed the buffer", i);
+    }
+    return 0;
+}
+
+extern "C" int xpngb_transform(xpngb_ctx* ctx, int op, xpngb_image* imgs, uint32_t n, const void* src, uint64_t size, int src_on_device,
+                               void* dst, int dst_on_device) {
+    if (!ctx) return 1;
+    ctx->err[0] = 0; ctx->launches = 0; ctx->last_ms = 0.f; ctx->cur = ctx->stream;
+    if (!imgs || !src || !dst) FAIL("null argument");
+    if (src == dst) FAIL("in-place orientation is not supported");
+    if (orient_check(ctx, op, imgs, n, size)) return 1;
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    const uint8_t* dsrc = (const uint8_t*)src;
+    if (!src_on_device) {
+        ENSURE(pixels, size);
+        CK(cudaMemcpyAsync(ctx->pixels.p, src, size, cudaMemcpyHostToDevice, ctx->stream));
+        dsrc = (const uint8_t*)ctx->pixels.p;
+    }
+    uint8_t* ddst = (uint8_t*)dst;
+    if (!dst_on_device) { ENSURE(oriented, size); ddst = (uint8_t*)ctx->oriented.p; }
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (orient_launch(ctx, op, imgs, n, dsrc, ddst)) return 1;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (!dst_on_device) CK(cudaMemcpyAsync(dst, ddst, size, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    return 0;
+}
+
+extern "C" int xpngb_encode_oriented(xpngb_ctx* ctx, int level, int op, xpngb_image* imgs, uint32_t n, const void* pixels,
+                                     uint64_t pixels_size, int pixels_on_device, void* out, uint64_t out_cap, int out_on_device,
+                                     uint64_t* out_offsets, uint64_t* out_sizes) {
+    if (!ctx) return 1;
+    ctx->err[0] = 0; ctx->cur = ctx->stream;
+    if (!imgs || !pixels) FAIL("null argument");
+    if (orient_check(ctx, op, imgs, n, pixels_size)) return 1;
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    const uint8_t* dsrc = (const uint8_t*)pixels;
+    if (!pixels_on_device) {
+        ENSURE(pixels, pixels_size);
+        CK(cudaMemcpyAsync(ctx->pixels.p, pixels, pixels_size, cudaMemcpyHostToDevice, ctx->stream));
+        dsrc = (const uint8_t*)ctx->pixels.p;
+    }
+    ENSURE(oriented, pixels_size);
+    if (orient_launch(ctx, op, imgs, n, dsrc, (uint8_t*)ctx->oriented.p)) return 1;
+    const uint32_t l0 = ctx->launches;
+    const int rc = xpngb_encode(ctx, level, imgs, n, ctx->oriented.p, pixels_size, 1, out, out_cap, out_on_device, out_offsets, out_sizes);
+    ctx->launches += l0;
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------

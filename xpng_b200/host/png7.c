@@ -216,12 +216,90 @@ _Bool png_store(const xpng_t *pm, const char *fn) {
     return bad;
 }
 
-/* 7/seven.c:39-79: ./seven --to_7 example.png example.7   |   ./seven --to_png example.7 example.png */
+/* ---------------------------------------------------------------------------------------------------------------
+ * Binary PPM (P6), the pixmap format of the reference's older front end (ancestor/gray.c:667-682, fed by
+ * `convert x.png x.ppm` in ancestor/test.rb:12) and of the sintel frames BASELINE.md quotes.
+ * ppm_load: "P6", then width, height, maxval separated by white space, '#' comments allowed, ONE white-space byte,
+ * then w*h*3 samples.  ancestor/gray.c:671-672 reads the two numbers with sscanf and takes the LAST w*h*3 bytes of the
+ * file as samples; for every file `convert` writes the two readings agree.  maxval must be 255 (8-bit samples, the only
+ * kind the .7 container holds); 16-bit and rescaled files are refused.
+ * ppm_store writes exactly the header of ancestor/gray.c:680: "P6\n%lu %lu\n255\n". */
+static int ppm_number(const u8_t *d, u64_t n, u64_t *pos, u64_t *val) {
+    u64_t i = *pos, v = 0, digits = 0;
+    for (;;) {                                   /* white space and comments before a number */
+        if (i >= n) return 1;
+        if (d[i] == '#') { while (i < n && d[i] != '\n' && d[i] != '\r') i++; continue; }
+        if (d[i] == ' ' || d[i] == '\t' || d[i] == '\n' || d[i] == '\r' || d[i] == '\v' || d[i] == '\f') { i++; continue; }
+        break;
+    }
+    while (i < n && d[i] >= '0' && d[i] <= '9') {
+        v = v * 10 + (u64_t)(d[i] - '0');
+        if (v > (1ull << 32)) return 1;
+        i++; digits++;
+    }
+    if (!digits) return 1;
+    *pos = i; *val = v;
+    return 0;
+}
+
+_Bool ppm_load(const char *fn, xpng_t *pm) {
+    u64_t n = 0, pos = 2, w = 0, h = 0, maxval = 0;
+    _Bool bad = 1;
+    u8_t *d;
+    if (!fn || !pm) return 1;
+    d = read_file(fn, &n);
+    if (!d) return 1;
+    if (n < 11 || d[0] != 'P' || d[1] != '6') goto done;
+    if (ppm_number(d, n, &pos, &w) || ppm_number(d, n, &pos, &h) || ppm_number(d, n, &pos, &maxval)) goto done;
+    if (maxval != 255 || !w || !h || w > (1u << 24) || h > (1u << 24)) goto done;
+    if (pos >= n || !(d[pos] == ' ' || d[pos] == '\t' || d[pos] == '\n' || d[pos] == '\r' || d[pos] == '\v' || d[pos] == '\f')) goto done;
+    pos++;
+    if (n - pos < w * h * 3) goto done;
+    pm->w = w; pm->h = h; pm->A = 0; pm->s = w * h * 3;
+    pm->p = malloc(pm->s);
+    if (!pm->p) goto done;
+    memcpy(pm->p, d + pos, pm->s);
+    bad = 0;
+done:
+    free(d);
+    return bad;
+}
+
+_Bool ppm_store(const xpng_t *pm, const char *fn) {
+    char hdr[100];
+    int l;
+    FILE *f;
+    _Bool bad;
+    if (!pm || !fn || !pm->p || !pm->w || !pm->h || pm->A || pm->s != pm->w * pm->h * 3) return 1;   /* P6 has no alpha */
+    l = sprintf(hdr, "P6\n%lu %lu\n255\n", (unsigned long)pm->w, (unsigned long)pm->h);
+    f = fopen(fn, "wb");
+    if (!f) return 1;
+    bad = fwrite(hdr, 1, (size_t)l, f) != (size_t)l || fwrite(pm->p, 1, pm->s, f) != pm->s;
+    return (_Bool)(fclose(f) != 0 || bad);
+}
+
+static _Bool is_ppm(const char *fn) {
+    u8_t m[2] = { 0, 0 };
+    FILE *f = fopen(fn, "rb");
+    if (!f) return 0;
+    if (fread(m, 1, 2, f) != 2) m[0] = 0;
+    fclose(f);
+    return m[0] == 'P' && m[1] == '6';
+}
+
+/* 7/seven.c:39-79: ./seven --to_7 example.png example.7   |   ./seven --to_png example.7 example.png
+ * Additions that leave the reference's contract alone: --to_7 also takes a P6 file (recognised by its magic), and
+ * --to_ppm example.7 example.ppm writes one (RGB only). */
 int seven_main(int argc, char **argv) {
     xpng_t pm;
     if (argc == 4 && !strcmp(argv[1], "--to_7")) {
+        if (is_ppm(argv[2])) return (int)(ppm_load(argv[2], &pm) || store_7(&pm, argv[3]));
         if (png_load(argv[2], &pm)) return 1;
         return (int)(normalize_rgba(&pm) || store_7(&pm, argv[3]));
+    }
+    if (argc == 4 && !strcmp(argv[1], "--to_ppm")) {
+        if (load_7(argv[2], &pm)) return 1;
+        return (int)ppm_store(&pm, argv[3]);
     }
     if (argc == 4 && !strcmp(argv[1], "--to_png")) {
         if (load_7(argv[2], &pm)) return 1;
