@@ -29,6 +29,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 W, H = 3840, 2160
 LEVELS = (1, 2, 7)
+# the levels of a step are independent jobs: level 2 (the longest chains) gets a host thread of its own, levels 1 and 7
+# share the second one (tools/e2e_probe.py: a third pipeline in flight only adds PCIe contention to level 2's copies)
+PIPELINES = ((2,), (1, 7))
 METRIC = "xpng encode+decode MPix/s over levels -1/-2/-7"
 
 
@@ -196,13 +199,13 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     # one codec context (= its own CUDA streams and scratch) per level: the three levels of a step are
-    # independent jobs, so they are issued concurrently from three host threads (ctypes drops the GIL)
+    # independent jobs, so they are issued concurrently from host threads, see PIPELINES (ctypes drops the GIL)
     cds = {lv: xpng_b200.Codec(local_rank) for lv in LEVELS}
     cd = cds[1]
     stream = torch.cuda.ExternalStream(cd.stream, device=dev)
     lib = xpng_b200.lib()
     from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=len(LEVELS))
+    pool = ThreadPoolExecutor(max_workers=len(PIPELINES))
 
     frame = synth.rgb(H, W, 1 + rank)
     npx = W * H
@@ -235,8 +238,8 @@ def run_ours(args, rank, world, local_rank):
         return cds[lv].last_launches
 
     def step(px, files, back, on_dev):
-        # one pipeline per level (encode, then decode of that level's file), the three pipelines in flight together
-        launches[0] += sum(pool.map(lambda lv: enc_one(lv, px, files, on_dev) + dec_one(lv, files, back, on_dev), LEVELS))
+        # per level: encode, then decode of that level's file; the pipelines of PIPELINES are in flight together
+        launches[0] += sum(pool.map(lambda lvs: sum(enc_one(lv, px, files, on_dev) + dec_one(lv, files, back, on_dev) for lv in lvs), PIPELINES))
 
     def timed(px, files, back, on_dev, steps, warmup):
         for _ in range(warmup):
@@ -361,7 +364,7 @@ def run_ours(args, rank, world, local_rank):
             "data": "synthetic",
             "config": {"workload": "configs[1]: one 3840x2160 RGB synthetic frame per GPU (seed 1+rank), levels -1/-2/-7, encode+decode",
                        "frames_per_gpu": 1, "tiles_per_frame": 45, "l2": "flushed between timed steps (256 MiB fill)",
-                       "concurrency": "the 3 levels of a step run as 3 concurrent encode->decode pipelines (one codec context and CUDA stream set per level)",
+                       "concurrency": "the 3 levels of a step run as 2 concurrent encode->decode pipelines: level 2 | level 1 then level 7 (one codec context and CUDA stream set per level)",
                        "parallelism": f"frames sharded over {world} GPU(s), no collective"},
             "e2e": {"value": round(e2e, 2), "unit": "MPix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_e2e / args.steps, 4)},

@@ -66,6 +66,62 @@ __global__ void k_mulhi64(uint32_t* out, long long* cyc, unsigned long long a) {
     long long t1 = clock64();
     out[threadIdx.x] = (uint32_t)x; if (!threadIdx.x) cyc[6] = t1 - t0;
 }
+// umul64hi with the four partial products independent of each other (the compiler's own sequence chains
+// xh*rl -> xl*rh+that -> xh*rh+that, three dependent IMAD.WIDE)
+__device__ __forceinline__ unsigned long long mulhi_par(unsigned long long x, uint32_t rl, uint32_t rh) {
+    const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 32);
+    const unsigned long long A = (unsigned long long)xh * rl, B = (unsigned long long)xl * rh, Cc = (unsigned long long)xl * rl,
+                             D = (unsigned long long)xh * rh;
+    const unsigned long long mid = (unsigned long long)(uint32_t)A + (uint32_t)B + (Cc >> 32);
+    return D + (A >> 32) + (B >> 32) + (mid >> 32);
+}
+__global__ void k_mulhi_par(uint32_t* out, long long* cyc, unsigned long long a) {
+    unsigned long long x = threadIdx.x + 0x123456789ull;
+    const uint32_t rl = (uint32_t)a, rh = (uint32_t)(a >> 32);
+    long long t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < N; i++) x = mulhi_par(x, rl, rh) + 0x9000000000000000ull;
+    long long t1 = clock64();
+    out[threadIdx.x] = (uint32_t)x; if (!threadIdx.x) cyc[12] = t1 - t0;
+}
+// same with add.cc chains written out
+__device__ __forceinline__ unsigned long long mulhi_ptx(unsigned long long x, uint32_t rl, uint32_t rh) {
+    const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 32);
+    uint32_t al, ah, bl, bh, ch, dl, dh, lo, hi;
+    asm("{\n\t.reg .u32 cl, m, c1;\n\t"
+        "mul.lo.u32 %0, %9, %10;\n\tmul.hi.u32 %1, %9, %10;\n\t"       // A = xh*rl
+        "mul.lo.u32 %2, %8, %11;\n\tmul.hi.u32 %3, %8, %11;\n\t"       // B = xl*rh
+        "mul.hi.u32 %4, %8, %10;\n\t"                                    // hi(C) = hi(xl*rl)
+        "mul.lo.u32 %5, %9, %11;\n\tmul.hi.u32 %6, %9, %11;\n\t"       // D = xh*rh
+        "add.cc.u32 m, %0, %2;\n\taddc.u32 c1, 0, 0;\n\t"
+        "add.cc.u32 m, m, %4;\n\taddc.u32 c1, c1, 0;\n\t"
+        "add.cc.u32 %5, %5, %1;\n\taddc.u32 %6, %6, 0;\n\t"
+        "add.cc.u32 %3, %3, c1;\n\taddc.u32 c1, 0, 0;\n\t"
+        "add.cc.u32 %5, %5, %3;\n\taddc.u32 %6, %6, c1;\n\t"
+        "mov.u32 %7, 0;\n\t}"
+        : "=&r"(al), "=&r"(ah), "=&r"(bl), "=&r"(bh), "=&r"(ch), "=&r"(dl), "=&r"(dh), "=&r"(lo)
+        : "r"(xl), "r"(xh), "r"(rl), "r"(rh));
+    (void)hi; (void)lo;
+    return ((unsigned long long)dh << 32) | dl;
+}
+__global__ void k_mulhi_ptx(uint32_t* out, long long* cyc, unsigned long long a) {
+    unsigned long long x = threadIdx.x + 0x123456789ull;
+    const uint32_t rl = (uint32_t)a, rh = (uint32_t)(a >> 32);
+    long long t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < N; i++) x = mulhi_ptx(x, rl, rh) + 0x9000000000000000ull;
+    long long t1 = clock64();
+    out[threadIdx.x] = (uint32_t)x; if (!threadIdx.x) cyc[13] = t1 - t0;
+}
+__global__ void k_mulhi_check(unsigned long long a, uint32_t* bad) {
+    unsigned long long x = (threadIdx.x + 1) * 0x9E3779B97F4A7C15ull + blockIdx.x * 0xD1B54A32D192ED03ull;
+    const uint32_t rl = (uint32_t)a, rh = (uint32_t)(a >> 32);
+    for (int i = 0; i < 4096; i++) {
+        const unsigned long long w = __umul64hi(x, a);
+        if (mulhi_par(x, rl, rh) != w || mulhi_ptx(x, rl, rh) != w) atomicAdd(bad, 1);
+        x = x * 6364136223846793005ull + 1442695040888963407ull + w;
+    }
+}
 __global__ void k_redux(uint32_t* out, long long* cyc) {
     uint32_t v = threadIdx.x;
     long long t0 = clock64();
@@ -127,11 +183,18 @@ int main() {
         k_ldg<<<1, 32>>>(g, out, cyc); k_imadwide<<<1, 32>>>(out, cyc, 77777); k_mulhi64<<<1, 32>>>(out, cyc, 0xF123456789ABCDEFull);
         k_redux<<<1, 32>>>(out, cyc); k_ballot<<<1, 32>>>(out, cyc); k_iadd<<<1, 32>>>(out, cyc, 5); k_popc<<<1, 32>>>(out, cyc, 3);
         k_switch<<<1, 32>>>(g8, out, cyc);
+        k_mulhi_par<<<1, 32>>>(out, cyc, 0xF123456789ABCDEFull); k_mulhi_ptx<<<1, 32>>>(out, cyc, 0xF123456789ABCDEFull);
         cudaDeviceSynchronize();
     }
     const char* names[] = { "shfl(idx=v)", "shfl(idx=v&15)", "lds32 chase", "lds64+and chase", "ldg L1 chase", "imad.wide+shift", "umul64hi+add",
-                            "redux.or(sel)", "ballot(cmp)", "xor+shr+add (3 alu)", "popc+add", "switch9+lds" };
-    for (int i = 0; i < 12; i++) printf("%-22s %7.2f cycles/iter\n", names[i], (double)cyc[i] / N);
+                            "redux.or(sel)", "ballot(cmp)", "xor+shr+add (3 alu)", "popc+add", "switch9+lds", "mulhi64 parallel (C)", "mulhi64 parallel (PTX)" };
+    {
+        uint32_t* bad; cudaMallocManaged(&bad, 4); *bad = 0;
+        k_mulhi_check<<<64, 256>>>(0xF123456789ABCDEFull, bad); k_mulhi_check<<<64, 256>>>(0x8000000000000001ull, bad);
+        k_mulhi_check<<<64, 256>>>(0xFFFFFFFFFFFFFFFFull, bad); cudaDeviceSynchronize();
+        printf("mulhi variants mismatches: %u\n", *bad);
+    }
+    for (int i = 0; i < 14; i++) printf("%-22s %7.2f cycles/iter\n", names[i], (double)cyc[i] / N);
     printf("err=%s\n", cudaGetErrorString(cudaGetLastError()));
     return 0;
 }

@@ -38,6 +38,8 @@ struct xpngb_ctx {
     float last_ms = 0.f;
     uint32_t launches = 0;
     uint64_t max_chunk_px = 1ull << 30;
+    uint32_t direct_max_tiles = 148;  // level-2 decode: tiles per call up to which the 64 KiB direct tables are used (3 chains per SM stay resident)
+    uint32_t v2_direct_max_tiles = ~0u;  // level-1 decode: same trade for the 16 KiB context tables
     uint32_t lat_max_blocks = 32768;  // entropy blocks per launch up to which the warp-per-block (latency) kernels are used (measured crossover, profiles/)
     // device scratch
     DevBuf pixels, norm, files, arena, tiles, imgs, seg_tile, costs, hist, seginfo, place, vplace, vcnt, sym_area,
@@ -182,7 +184,7 @@ static int upload_plan(xpngb_ctx* ctx, const Plan& P) {
 // Shared memory per entropy-block CTA = cum[] + tables + word ring.  Tables are sized per launch so that every
 // chain of a frame is resident at once (one level: 4 B x 2^PROB_BITS; two levels: 1 KiB + 2^PROB_BITS bytes).
 constexpr uint32_t lat_smem(uint32_t lut_bytes) { return LAT_CUM_WORDS * 4 + lut_bytes + LAT_RING_WORDS * 4; }
-constexpr uint32_t LUT_ONE_12 = 4u << 12, LUT_ONE_14 = 4u << 14, LUT_TWO_14 = 1024 + (1u << 14), LUT_TWO_15 = 1024 + (1u << 15);
+constexpr uint32_t LUT_ONE_12 = 4u << 12, LUT_ONE_14 = 4u << 14, LUT_TWO_12 = 1024 + (1u << 12), LUT_TWO_14 = 1024 + (1u << 14), LUT_TWO_15 = 1024 + (1u << 15);
 
 static void m2_set_attributes() {
     auto k_big = k_rans_v1<256, 32>;
@@ -214,13 +216,17 @@ static int m2_encode_tiles(xpngb_ctx* ctx, const Plan& P, uint32_t ntiles, uint3
                    (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->blocks.p, (uint32_t*)ctx->tabs.p, ntiles, 0, 17, 0, 0 };
     if (17 * ntiles <= ctx->lat_max_blocks * 5 / 2) {   // level 2 crosses over later than level 1 (profiles/: ~600 vs ~380 frames of 1080p)
         auto k_rans_v1_pair_16 = k_rans_v1_pair<16>; auto k_rans_v1_pair_256 = k_rans_v1_pair<256>;
-        FORK_SIDE(0);                                 // alphabets above 16 symbols and the grey candidates: side stream
+        // alphabets above 16 symbols and the grey candidates go to a side stream that forks BEFORE the main launch but is
+        // fed AFTER it: the small-alphabet kernel holds the longest chains, and in a batch its CTAs must be placed first
+        // (the 98 KiB CTAs of the other kernel would otherwise take the shared memory and delay them)
+        FORK_SIDE(0);
+        BACK_TO_MAIN();
+        LAUNCH(k_rans_v1_pair_16, (17 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 17 * PAIR_BLK * 24, ra);
+        ctx->cur = ctx->side[0];
         RansV1Args rb = ra; rb.c0 = 9; rb.nc = 8; rb.nmin = 16;
         LAUNCH(k_rans_v1_pair_256, (8 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, rb);
         rb.c0 = 0; rb.nc = 4; rb.nmin = 0; rb.grey = 1;
         LAUNCH(k_rans_v1_pair_256, (4 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, rb);
-        BACK_TO_MAIN();
-        LAUNCH(k_rans_v1_pair_16, (17 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 17 * PAIR_BLK * 24, ra);
         JOIN_SIDE(0);
     } else {
     auto k_rans_v1_lane_16 = k_rans_v1<16, 128>; auto k_rans_v1_lane_256 = k_rans_v1<256, 32>;
@@ -263,6 +269,8 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     { auto k_big = k_rans_v2<256, 32>; cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 16); }
     m2_set_attributes();
     if (const char* e = getenv("XPNGB_LAT_MAX_BLOCKS")) ctx->lat_max_blocks = (uint32_t)atol(e);
+    if (const char* e = getenv("XPNGB_V2_DIRECT_MAX_TILES")) ctx->v2_direct_max_tiles = (uint32_t)atol(e);
+    if (const char* e = getenv("XPNGB_DIRECT_MAX_TILES")) ctx->direct_max_tiles = (uint32_t)atol(e);
     { auto p = k_rans_v2_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * PAIR_BLK * 24); }
     { auto p = k_rans_v1_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * PAIR_BLK * 24); }
     cudaFuncSetAttribute(k_dec_unpredict_rows<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2 * 32 * UNR_PITCH);
@@ -442,13 +450,16 @@ static int encode_chunk(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32_t n
         if (9 * ntiles <= ctx->lat_max_blocks) {
             auto k_rans_v2_pair_16 = k_rans_v2_pair<16>; auto k_rans_v2_pair_256 = k_rans_v2_pair<256>;
             if (P.any_rgba) {                          // the alpha blocks are independent of the context blocks: side stream
-                RansV2Args rb = ra; rb.c0 = 9; rb.nc = 1;
-                FORK_SIDE(0);
-                LAUNCH(k_rans_v2_pair_256, (ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, rb);
+                FORK_SIDE(0);                          // forks before, is fed after the main launch (see m2_encode_tiles)
                 BACK_TO_MAIN();
             }
             LAUNCH(k_rans_v2_pair_16, (9 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 17 * PAIR_BLK * 24, ra);
-            if (P.any_rgba) JOIN_SIDE(0);
+            if (P.any_rgba) {
+                RansV2Args rb = ra; rb.c0 = 9; rb.nc = 1;
+                ctx->cur = ctx->side[0];
+                LAUNCH(k_rans_v2_pair_256, (ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, rb);
+                JOIN_SIDE(0);
+            }
         } else {
         auto k_rans_v2_lane_9 = k_rans_v2<9, 128>; auto k_rans_v2_lane_256 = k_rans_v2<256, 32>;
         LAUNCH(k_rans_v2_lane_9, (9 * ntiles + 127) / 128, 128, 9 * 128 * 16, ra);
@@ -761,7 +772,8 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
             LAUNCH(k_dec_rows_rgba, ntiles, 32, 0, d_tiles, d_imgs, (const DecTile*)d_dt, (const uint32_t*)ctx->rowcnt.p, (RowInfo*)ctx->rows.p);
         }
         ctx->cur = f1;
-        if (lat) LAUNCH(k_dec_rans_v2_lat, 9 * ntiles, 32, lat_smem(LUT_ONE_12), ra, LUT_ONE_12);
+        const uint32_t lut12 = ntiles <= ctx->v2_direct_max_tiles ? LUT_ONE_12 : LUT_TWO_12;
+        if (lat) LAUNCH(k_dec_rans_v2_lat, 9 * ntiles, 32, lat_smem(lut12), ra, lut12);
         else LAUNCH(k_dec_rans_v2_small<128>, (9 * ntiles + 127) / 128, 128, 0, ra);
         if (launch_walk(1)) return 1;
         BACK_TO_MAIN();
@@ -771,12 +783,16 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
         if (17 * ntiles <= ctx->lat_max_blocks * 5 / 2) {
             // value streams on the side streams (joined before the residual kernels); LAT_M2_ORDER: 0..2 alphabets of at
             // most 16 symbols (direct table, 64 KiB), 3..7 larger alphabets (two-level), 8..16 contexts, 17 grey plane
-            RansV1LatArgs la{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 3, LUT_ONE_14, 0u, ~0u };
+            // a batch with more chains than fit next to 64 KiB tables (3 per SM) trades the shorter dependent step of the
+            // direct table for residency: two-level tables (17 KiB) keep 12 chains per SM
+            const bool direct = ntiles <= ctx->direct_max_tiles;
+            const uint32_t lut16 = direct ? LUT_ONE_14 : LUT_TWO_14;
+            RansV1LatArgs la{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 3, lut16, 0u, ~0u };
             auto k_dec_rans_v1_lat_values16 = k_dec_rans_v1_lat; auto k_dec_rans_v1_lat_values256 = k_dec_rans_v1_lat;
             auto k_dec_rans_v1_lat_grey = k_dec_rans_v1_lat; auto k_dec_rans_v1_lat_ctx = k_dec_rans_v1_lat;   // names for the profile report
             auto k_dec_rans_v1_lat_ctx_short = k_dec_rans_v1_lat;
             FORK_SIDE(0); side_busy[0] = true;
-            LAUNCH(k_dec_rans_v1_lat_values16, 3 * ntiles, 32, lat_smem(LUT_ONE_14), la);
+            LAUNCH(k_dec_rans_v1_lat_values16, 3 * ntiles, 32, lat_smem(lut16), la);
             FORK_SIDE(1); side_busy[1] = true;
             la.j0 = 3; la.nj = 5; la.lut_bytes = LUT_TWO_14;
             LAUNCH(k_dec_rans_v1_lat_values256, 5 * ntiles, 32, lat_smem(LUT_TWO_14), la);
@@ -786,13 +802,15 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
             // context streams: the few long ones (they bound the walk's start on real images) get the 64 KiB direct table,
             // the many short ones a two-level table on a side stream, so that everything stays resident
             constexpr uint32_t CTX_LONG = 24576;
-            la.j0 = 8; la.nj = 9; la.lut_bytes = LUT_TWO_14; la.n_lo = 0; la.n_hi = CTX_LONG;
-            FORK_SIDE(4); side_busy[4] = true;
-            LAUNCH(k_dec_rans_v1_lat_ctx_short, 9 * ntiles, 32, lat_smem(LUT_TWO_14), la);
-            BACK_TO_MAIN();
-            la.lut_bytes = LUT_ONE_14; la.n_lo = CTX_LONG; la.n_hi = ~0u;
-            LAUNCH(k_dec_rans_v1_lat_ctx, 9 * ntiles, 32, lat_smem(LUT_ONE_14), la);
-            JOIN_SIDE(4); side_busy[4] = false;           // the walk needs every context stream
+            la.j0 = 8; la.nj = 9; la.lut_bytes = LUT_TWO_14; la.n_lo = 0; la.n_hi = direct ? CTX_LONG : ~0u;
+            if (direct) {
+                FORK_SIDE(4); side_busy[4] = true;
+                LAUNCH(k_dec_rans_v1_lat_ctx_short, 9 * ntiles, 32, lat_smem(LUT_TWO_14), la);
+                BACK_TO_MAIN();
+                la.lut_bytes = LUT_ONE_14; la.n_lo = CTX_LONG; la.n_hi = ~0u;
+                LAUNCH(k_dec_rans_v1_lat_ctx, 9 * ntiles, 32, lat_smem(LUT_ONE_14), la);
+                JOIN_SIDE(4); side_busy[4] = false;       // the walk needs every context stream
+            } else LAUNCH(k_dec_rans_v1_lat_ctx, 9 * ntiles, 32, lat_smem(LUT_TWO_14), la);
         } else {
         RansV1DecArgs rv{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 9, 0, 16 };
         auto k_dec_rans_v1_lane_8 = k_dec_rans_v1_small<8, 128>; auto k_dec_rans_v1_lane_15 = k_dec_rans_v1_small<15, 128>; auto k_dec_rans_v1_lane_big = k_dec_rans_v1_big<32>;
