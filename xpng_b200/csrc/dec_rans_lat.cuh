@@ -350,8 +350,18 @@ __global__ void __launch_bounds__(WARPS * 32) k_dec_walk_lat(WalkArgs A) {
                 nbuf = need ? walk_pack8(raw) : nbuf;
                 const uint32_t doload = (need && ch < nch) ? 1u : 0u;
                 raw.x = need ? 0u : raw.x; raw.y = need ? 0u : raw.y;
+#ifndef XPB_WALK_PF
+#define XPB_WALK_PF 16
+#endif
+                // the load is consumed 8 steps (~400 cycles) later: enough for an L1 hit, not for a miss, and a miss stalls
+                // the whole in-order chain.  So the line after next is requested from L2 now (a line = 16 chunks).
+#if XPB_WALK_PF > 0
+                asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %3, 0;\n @q ld.global.nc.v2.u32 {%0, %1}, [%2];\n @q prefetch.global.L1 [%4];\n}"
+                             : "+r"(raw.x), "+r"(raw.y) : "l"(src + ch), "r"(doload), "l"(src + min(ch + XPB_WALK_PF, nch - 1)));
+#else
                 asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %3, 0;\n @q ld.global.nc.v2.u32 {%0, %1}, [%2];\n}"
                              : "+r"(raw.x), "+r"(raw.y) : "l"(src + ch), "r"(doload));
+#endif
                 ch += need ? 1u : 0u;
             }
         }
@@ -414,6 +424,96 @@ __global__ void __launch_bounds__(32) k_dec_walk_smem(WalkArgs A) {
                 wlo |= (uint32_t)add; whi |= (uint32_t)(add >> 32);
                 cnt += nm & 8u;
                 nx = src[min(ch, nch)];                                 // word nch is the zero pad; consumed four steps later
+                ch += nm & 1u;
+            }
+            if ((j & 7) == 5) nbuf = (nx & nm) | (nbuf & ~nm);
+        }
+        if (pos + lane < m) out[pos + lane] = (uint8_t)keep;
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Same walk for tiles whose streams do not all fit next to each other in shared memory (batches, tiles above
+// WALK_SMEM_MAX_SYMS): every context stream gets a small RING of nibble-packed chunks in shared memory, and the warp
+// keeps the rings topped up between groups of 32 steps — one coalesced 256-byte read per refill, loaded during one
+// group and packed / stored at the start of the next, so its memory latency never meets the chain.  The 32 steps of a
+// group are the loop of k_dec_walk_smem (fixed-latency shared loads only).
+//   ring: WRING_CH chunks of 8 symbols per stream; lane k < 9 owns stream k: ch = next chunk it will pop into its
+//   window, st = chunks staged.  One refill (32 chunks) per group at most, for the first stream with st - ch <=
+//   WRING_LOW.  A stream pops at most 4 chunks per group, nine needy streams are served within 9 groups (+1 group of
+//   load latency): 40 < WRING_LOW chunks, so a staged chunk is always ahead of ch; st - ch <= WRING_LOW + 32 <
+//   WRING_CH, so a refill never overwrites an unread chunk.
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t WRING_CH = 128, WRING_LOW = 64;
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_dec_walk_ring(WalkArgs A) {
+    __shared__ uint32_t wring[WARPS][9][WRING_CH];
+    const uint32_t wid = threadIdx.x >> 5, tile = blockIdx.x * WARPS + wid, lane = threadIdx.x & 31;
+    if (tile >= A.ntiles) return;
+    const TileDesc t = A.tiles[tile];
+    if (A.imgs[t.img].mode != A.mode) return;
+    const DecTile* d = A.dt + tile;
+    if (d->m == 0 || d->m >= 0x20) return;   // raw / grey / single colour / failed
+    uint8_t* out = A.nlseq + t.px_off;
+    const uint32_t m = d->nsym;
+    const uint32_t c = lane < 9 ? lane : 0;
+    const uint32_t nch = lane < 9 ? (d->blk[c].n + 7) / 8 : 0;   // 8-symbol chunks of my stream
+    const uint2* gsrc = reinterpret_cast<const uint2*>(A.streams + t.str_off + d->blk[c].soff);
+    uint32_t* myring = wring[wid][c];
+    uint32_t st = 0, ch = 0;
+    // one refill of stream p: 32 chunks from chunk index s0 (all lanes)
+    auto fetch = [&](uint32_t p, uint2& r) {
+        const uint2* base = reinterpret_cast<const uint2*>(__shfl_sync(0xffffffffu, (unsigned long long)gsrc, p));
+        const uint32_t s0 = __shfl_sync(0xffffffffu, st, p), np = __shfl_sync(0xffffffffu, nch, p);
+        const uint32_t k = s0 + lane;
+        r = k < np ? __ldg(base + k) : make_uint2(0u, 0u);
+    };
+    auto store = [&](uint32_t p, const uint2 r) {
+        const uint32_t s0 = __shfl_sync(0xffffffffu, st, p);
+        wring[wid][p][(s0 + lane) & (WRING_CH - 1)] = walk_pack8(r);
+        if (lane == p) st += 32;
+    };
+    auto needy = [&]() -> uint32_t { return __ballot_sync(0xffffffffu, lane < 9 && st < nch && st - ch <= WRING_LOW); };
+    // initial fill: up to three refills per stream
+    for (uint32_t nb = needy(); nb; nb = needy()) {
+        const uint32_t p = __ffs(nb) - 1;
+        uint2 r; fetch(p, r); store(p, r);
+    }
+    __syncwarp();
+    auto chunk = [&](uint32_t k) -> uint32_t { const uint32_t v = myring[k & (WRING_CH - 1)]; return k < nch ? v : 0u; };
+    uint32_t wlo = chunk(0), whi = chunk(1), cnt = 16, nbuf = chunk(2);
+    ch = 3;
+    uint32_t info = wlo & 0xFu, cur = 0, nm = 0, nx = 0;
+    uint32_t mk[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) { mk[j] = lane == (uint32_t)j ? 0xFFFFFFFFu : 0u; asm volatile("" : "+r"(mk[j])); }
+    uint32_t pend = 32;                                     // stream whose refill is in flight (32 = none)
+    uint2 preg = make_uint2(0u, 0u);
+    for (uint32_t pos = 0; pos < m; pos += 32) {
+        // between groups (warp-uniform): land the refill loaded during the previous group, start the next one
+        if (pend < 32) { store(pend, preg); __syncwarp(); }
+        {
+            const uint32_t nb = needy();
+            pend = nb ? __ffs(nb) - 1 : 32u;
+            if (nb) fetch(pend, preg);
+        }
+        uint32_t keep = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const uint32_t got = __shfl_sync(0xffffffffu, info, cur);   // the chain: one shuffle per symbol
+            const bool own = lane == cur;                               // the owner pops while the shuffle is in flight
+            const uint32_t plo = __funnelshift_r(wlo, whi, 4), phi = whi >> 4;
+            wlo = own ? plo : wlo; whi = own ? phi : whi; cnt -= own ? 1u : 0u;
+            info = wlo & 0xFu;
+            keep |= got & mk[j];
+            cur = got;
+            if ((j & 7) == 1) {                                         // see k_dec_walk_smem
+                nm = cnt <= 8u ? 0xFFFFFFFFu : 0u;
+                const unsigned long long add = (unsigned long long)(nbuf & nm) << (4u * min(cnt, 8u));
+                wlo |= (uint32_t)add; whi |= (uint32_t)(add >> 32);
+                cnt += nm & 8u;
+                nx = chunk(ch);                                         // consumed four steps later
                 ch += nm & 1u;
             }
             if ((j & 7) == 5) nbuf = (nx & nm) | (nbuf & ~nm);
