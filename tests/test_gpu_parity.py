@@ -180,9 +180,39 @@ def test_throughput_kernel_family(monkeypatch):
         cd.close()
 
 
-def test_largest_tile_uses_global_walk(codec):
+def test_batch_decode_variants(monkeypatch):
+    """Decode variants that batches select by residency (ring-staged context walk, two-level tables for every level-2
+    block), forced here on small inputs: same pixels, and corrupt files neither fault nor poison the context."""
+    import xpng_b200
+    monkeypatch.setenv("XPNGB_WALK", "ring")
+    monkeypatch.setenv("XPNGB_DIRECT_MAX_TILES", "0")
+    cd = xpng_b200.Codec(0)
+    try:
+        imgs = [synth.rgb(700, 900, 91), synth.rgba(450, 460, 92), synth.gray_as_rgb(300, 520, 93), synth.noise(90, 70, 94),
+                synth.rgb(5, 2000, 95), synth.sintel_like(1003)]
+        for lv in (1, 2):
+            want = [po.encode(lv, im) for im in imgs]
+            for b, im in zip(cd.decode(want), imgs):
+                assert np.array_equal(b, po.normalize(im)), (lv, im.shape)
+        rng = np.random.default_rng(12)
+        for lv, img in ((1, imgs[1]), (2, imgs[0]), (1, imgs[5])):
+            good = po.encode(lv, img)
+            for k in range(24):
+                f = bytearray(good)
+                for _ in range(int(rng.integers(1, 6))):
+                    f[int(rng.integers(8, len(f)))] = int(rng.integers(0, 256))
+                try:
+                    cd.decode([bytes(f)])
+                except RuntimeError:
+                    pass
+            assert np.array_equal(cd.decode([good])[0], po.normalize(img))
+    finally:
+        cd.close()
+
+
+def test_largest_tile_uses_ring_walk(codec):
     """A 666 x 666 image is ONE tile (libxpng.c:57-80) of 443 556 pixels: its context streams do not fit the
-    shared-memory walk, so the register-window walk over global memory runs instead."""
+    shared-memory walk, so the ring-staged walk (k_dec_walk_ring) runs instead."""
     px = synth.rgb(666, 666, 91)
     for lv in (1, 2):
         want = po.encode(lv, px)

@@ -38,7 +38,7 @@ struct xpngb_ctx {
     float last_ms = 0.f;
     uint32_t launches = 0;
     uint64_t max_chunk_px = 1ull << 30;
-    bool walk_global = false;
+    bool walk_global = false, walk_ring = false;   // XPNGB_WALK=global | ring: force a walk variant (tests, A/B)
     uint32_t direct_max_tiles = 148;  // level-2 decode: tiles per call up to which the 64 KiB direct tables are used (3 chains per SM stay resident)
     uint32_t v2_direct_max_tiles = ~0u;  // level-1 decode: same trade for the 16 KiB context tables
     uint32_t lat_max_blocks = 32768;  // entropy blocks per launch up to which the warp-per-block (latency) kernels are used (measured crossover, profiles/)
@@ -271,7 +271,7 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     m2_set_attributes();
     if (const char* e = getenv("XPNGB_LAT_MAX_BLOCKS")) ctx->lat_max_blocks = (uint32_t)atol(e);
     if (const char* e = getenv("XPNGB_V2_DIRECT_MAX_TILES")) ctx->v2_direct_max_tiles = (uint32_t)atol(e);
-    if (const char* e = getenv("XPNGB_WALK")) ctx->walk_global = !strcmp(e, "global");
+    if (const char* e = getenv("XPNGB_WALK")) { ctx->walk_global = !strcmp(e, "global"); ctx->walk_ring = !strcmp(e, "ring"); }
     if (const char* e = getenv("XPNGB_DIRECT_MAX_TILES")) ctx->direct_max_tiles = (uint32_t)atol(e);
     { auto p = k_rans_v2_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * PAIR_BLK * 24); }
     { auto p = k_rans_v1_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * PAIR_BLK * 24); }
@@ -751,7 +751,7 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
         WalkArgs wa{ d_tiles, d_imgs, d_dt, (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->nlseq.p, ntiles, mode };
         // the shared-memory walk only pays when every tile's CTA is resident at once (no waves): 227 KB per SM, 148 SMs
         const uint32_t resident = 148u * ((227u * 1024u) / (wsm + 1024u));
-        if (ntiles <= resident && maxpx <= WALK_SMEM_MAX_SYMS) LAUNCH(k_dec_walk_smem<0>, ntiles, 32, wsm, wa);
+        if (ntiles <= resident && maxpx <= WALK_SMEM_MAX_SYMS && !ctx->walk_ring && !ctx->walk_global) LAUNCH(k_dec_walk_smem<0>, ntiles, 32, wsm, wa);
         else if (ctx->walk_global) {                   // XPNGB_WALK=global: the older variant with refills straight from global memory
             if (ntiles <= 592) LAUNCH(k_dec_walk_lat<1>, ntiles, 32, 0, wa);
             else LAUNCH(k_dec_walk_lat<4>, (ntiles + 3) / 4, 128, 0, wa);
