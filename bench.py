@@ -195,7 +195,10 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        torch.cuda.set_device(local_rank)
+        # the communicator is created here (eagerly, or by the barrier): NCCL announces its version on stdout, which must
+        # carry ONE JSON line, so fd 1 points at /dev/null meanwhile
+        _quiet_call(lambda: (dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank)), dist.barrier()))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     # one codec context (= its own CUDA streams and scratch) per level: the three levels of a step are
