@@ -240,9 +240,11 @@ static int m2_encode_tiles(xpngb_ctx* ctx, const Plan& P, uint32_t ntiles, uint3
     LAUNCH(k_m2_finish, (ntiles + 127) / 128, 128, 0, d_tiles, (const uint8_t*)ctx->tclass.p, (TileState*)ctx->state.p, ntiles);
     return 0;
 }
+// CTAs per tile for the assembly kernels: a single frame has fewer tiles than SMs, so each tile's copies are sliced
+static unsigned assemble_split(uint32_t ntiles) { const uint32_t y = 592u / (ntiles ? ntiles : 1u); return y < 1u ? 1u : (y > 8u ? 8u : y); }
 static int m2_assemble(xpngb_ctx* ctx, const AssembleArgs& aa, uint32_t ntiles) {
     AssembleM2Args ma{ aa, (const uint8_t*)ctx->tclass.p, (const uint32_t*)ctx->tabs.p, (const uint8_t*)ctx->streams.p };
-    LAUNCH(k_assemble_m2, ntiles, 256, 0, ma);
+    LAUNCH(k_assemble_m2, dim3(ntiles, assemble_split(ntiles)), 256, 0, ma);
     return 0;
 }
 
@@ -480,7 +482,7 @@ static int encode_chunk(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32_t n
         AssembleArgs aa{ d_imgs, d_tiles, (const TileState*)ctx->state.p, (const ImageOut*)ctx->outs.p, (const SegInfo*)ctx->seginfo.p,
                          (const SegPlace*)ctx->place.p, nullptr, (const uint8_t*)ctx->bits_area.p, (const uint8_t*)ctx->blocks.p, dout };
         if (any2) { if (m2_assemble(ctx, aa, ntiles)) return 1; }
-        else LAUNCH(k_assemble_m1, ntiles, 256, 0, aa);
+        else LAUNCH(k_assemble_m1, dim3(ntiles, assemble_split(ntiles)), 256, 0, aa);
     }
     if (ensure_pin(ctx, ctx->pin_b, n * sizeof(ImageOut))) return 1;
     CK(cudaMemcpyAsync(ctx->pin_b.p, ctx->outs.p, n * sizeof(ImageOut), cudaMemcpyDeviceToHost, ctx->stream));

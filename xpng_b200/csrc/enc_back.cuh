@@ -368,6 +368,19 @@ __device__ __forceinline__ void copy_bytes(uint8_t* dst, const uint8_t* src, uin
     } else for (uint64_t k = threadIdx.x; k < n; k += blockDim.x) dst[k] = src[k];
 }
 
+// Slice `part` of `nparts` of the same copy (a tile's assembly is spread over gridDim.y CTAs when tiles are few).
+__device__ __forceinline__ void copy_bytes_part(uint8_t* dst, const uint8_t* src, uint64_t n, uint32_t part, uint32_t nparts) {
+    if (nparts == 1) { copy_bytes(dst, src, n); return; }
+    if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 3u) == 0) {
+        const uint64_t nw = n >> 2, lo = nw * part / nparts, hi = nw * (part + 1) / nparts;
+        for (uint64_t k = lo + threadIdx.x; k < hi; k += blockDim.x) reinterpret_cast<uint32_t*>(dst)[k] = reinterpret_cast<const uint32_t*>(src)[k];
+        if (part == 0) for (uint64_t k = (nw << 2) + threadIdx.x; k < n; k += blockDim.x) dst[k] = src[k];
+    } else {
+        const uint64_t lo = n * part / nparts, hi = n * (part + 1) / nparts;
+        for (uint64_t k = lo + threadIdx.x; k < hi; k += blockDim.x) dst[k] = src[k];
+    }
+}
+
 __device__ __forceinline__ void copy_tile_rows(uint8_t* dst, uint64_t dst_pitch, const uint8_t* src, const TileDesc& t) {
     const uint32_t rowb = t.w * t.pxsz;
     for (uint32_t y = threadIdx.x >> 5; y < t.h; y += blockDim.x >> 5)
@@ -432,6 +445,8 @@ __global__ void __launch_bounds__(256) k_assemble_m1(AssembleArgs A) {
     const TileState* st = A.state + tile;
     uint8_t* file = A.out + O.off;
     const uint8_t* src = A.px + t.src_off;
+    const uint32_t part = blockIdx.y, nparts = gridDim.y;        // coded tiles: the bit gather and the block copies are sliced over gridDim.y CTAs
+    if (part && ((O.mode & 0x100) || (O.mode & 0xFF) == 7 || st->kind == 0)) return;
     if (assemble_common(t, I, O, file, src)) return;
     uint8_t* blob = file + st->out_off;
     if (st->kind == 0) {          // raw tile (libxpng.c:566-567)
@@ -442,7 +457,7 @@ __global__ void __launch_bounds__(256) k_assemble_m1(AssembleArgs A) {
     const uint64_t kbits = (uint64_t)st->kbits_lo | ((uint64_t)st->kbits_hi << 32);
     const uint32_t kwords = (uint32_t)((kbits + 31) / 32);
     if (tid == 0) {
-        st32u(blob, (1u << 28) + (st->pr << 24) + st->size); st32u(blob + 4, 4 + 4 * kwords);
+        if (part == 0) { st32u(blob, (1u << 28) + (st->pr << 24) + st->size); st32u(blob + 4, 4 + 4 * kwords); }
         uint32_t fp = 0;            // first pixel, MSB first (libxpng.c:547), left-aligned in one word
         for (uint32_t c = 0; c < t.pxsz; c++) fp = (fp << 8) | src[c];
         fpw = fp << (32 - 8 * t.pxsz);
@@ -453,12 +468,12 @@ __global__ void __launch_bounds__(256) k_assemble_m1(AssembleArgs A) {
         sptr[j + 1] = reinterpret_cast<const uint32_t*>(A.bits_area + (uint64_t)(t.seg0 + j) * SEG_BITS_BYTES);
     }
     __syncthreads();
-    for (uint32_t wi = tid; wi < kwords; wi += 256) st32u(blob + 8 + 4ull * wi, gather_word(wi, t.nseg + 1, sbit, snb, sptr));
+    for (uint32_t wi = part * 256 + tid; wi < kwords; wi += 256 * nparts) st32u(blob + 8 + 4ull * wi, gather_word(wi, t.nseg + 1, sbit, snb, sptr));
     // entropy blocks
     uint8_t* dst = blob + 8 + 4ull * kwords;
     const uint8_t* bsrc = A.blocks + block_slice(t, tile);
     for (int c = 0; c < (t.pxsz == 4 ? 10 : 9); c++) {
-        copy_bytes(dst, bsrc + st->boff[c], st->bsize[c]);
+        copy_bytes_part(dst, bsrc + st->boff[c], st->bsize[c], part, nparts);
         dst += st->bsize[c];
     }
 }

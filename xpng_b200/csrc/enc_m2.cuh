@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(256) k_m2_classify(const TileDesc* __restrict_
     int single = 1, grey = 1;
     const uint32_t first = f0 | (f1 << 8) | (f2 << 16), wq = 3 * t.w >= 16 ? (3 * t.w - 16) / 12 + 1 : 0;   // 16-byte windows inside the row
     for (uint32_t y = threadIdx.x >> 5; y < t.h; y += 8) {
+        if (!__any_sync(0xffffffffu, single | grey)) break;              // this warp has seen a pixel that rules out both classes: the tile is RGB
         const uint8_t* row = src + (uint64_t)y * t.bpr;
         for (uint32_t g = threadIdx.x & 31; g < wq; g += 32) {           // four pixels per lane and iteration (ld_rgb4)
             uint32_t v[4]; ld_rgb4(row + 12 * g, v);
@@ -265,6 +266,8 @@ __global__ void __launch_bounds__(256) k_assemble_m2(AssembleM2Args M) {
     const TileState* st = A.state + tile;
     uint8_t* file = A.out + O.off;
     const uint8_t* src = A.px + t.src_off;
+    const uint32_t part = blockIdx.y, nparts = gridDim.y;        // RGB tiles: the side-stream gather and the 17 block copies are sliced over gridDim.y CTAs
+    if (part && ((O.mode & 0x100) || (O.mode & 0xFF) == 7 || st->kind != 2)) return;
     if (assemble_common(t, I, O, file, src)) return;
     uint8_t* blob = file + st->out_off;
     const uint8_t* bsrc = A.blocks + t.blk_off;
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(256) k_assemble_m2(AssembleM2Args M) {
     // RGB: [hdr][bsz][shared side stream][9 context blocks][8 value blocks]   (libxpng.c:680-683)
     const uint32_t bits = st->kbits_lo, words = (bits + 31) / 32;
     if (tid == 0) {
-        st32u(blob, st->size + (1u << 28) + (st->pr << 24)); st32u(blob + 4, 4 + 4 * words);
+        if (part == 0) { st32u(blob, st->size + (1u << 28) + (st->pr << 24)); st32u(blob + 4, 4 + 4 * words); }
         fpw = ((uint32_t)src[0] << 24) | ((uint32_t)src[1] << 16) | ((uint32_t)src[2] << 8);
         sbit[0] = 0; snb[0] = 24; sptr[0] = &fpw;
     }
@@ -310,9 +313,9 @@ __global__ void __launch_bounds__(256) k_assemble_m2(AssembleM2Args M) {
         sptr[tid + 1] = st->btype[tid] == 2 ? reinterpret_cast<const uint32_t*>(bsrc + st->breg[tid]) : M.tabs + ((uint64_t)tile * 17 + tid) * TAB_WORDS;
     }
     __syncthreads();
-    for (uint32_t wi = tid; wi < words; wi += 256) st32u(blob + 8 + 4ull * wi, gather_word(wi, 18, sbit, snb, sptr));
+    for (uint32_t wi = part * 256 + tid; wi < words; wi += 256 * nparts) st32u(blob + 8 + 4ull * wi, gather_word(wi, 18, sbit, snb, sptr));
     uint8_t* dst = blob + 8 + 4ull * words;
-    for (int c = 0; c < 17; c++) { copy_bytes(dst, bsrc + st->boff[c], st->bsize[c]); dst += st->bsize[c]; }
+    for (int c = 0; c < 17; c++) { copy_bytes_part(dst, bsrc + st->boff[c], st->bsize[c], part, nparts); dst += st->bsize[c]; }
 }
 
 }  // namespace xpb
