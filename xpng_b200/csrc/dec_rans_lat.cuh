@@ -22,11 +22,12 @@ namespace xpb {
 
 // Renormalisation words are staged through a shared-memory ring by the whole warp (bulk, coalesced,
 // misalignment removed with a funnel shift, zeros past the end: libxpng.c:295, :475), so that the
-// chain reads them with fixed-latency shared loads.  Slot LAT_RING mirrors slot 0 (the chain reads the
-// pair ring[k], ring[k + 1] without wrapping the second index).
+// chain reads them with fixed-latency shared loads.  The first LAT_TAIL slots are mirrored behind the ring, so the ring
+// offset is wrapped once per group of 32 symbols and only grows inside it (two instructions less per symbol pair).
 constexpr uint32_t LAT_RING = 512;               // words; refilled in halves (a group of 32 symbols consumes at most 32)
 constexpr uint32_t LAT_HALF = LAT_RING / 2;
-constexpr uint32_t LAT_RING_WORDS = LAT_RING + 4;
+constexpr uint32_t LAT_TAIL = 36;                // slots 0 .. LAT_TAIL-1 are mirrored behind the ring: a group reads up to 33 words past its start without wrapping
+constexpr uint32_t LAT_RING_WORDS = LAT_RING + LAT_TAIL;
 
 template <int DIR>
 struct WordSrc {
@@ -60,7 +61,7 @@ struct WordSrc {
             const uint32_t v = k < nwords ? __funnelshift_r(a0[i], a1[i], sh) : 0u;
             const uint32_t slot = k & (LAT_RING - 1);
             ring[slot] = v;
-            if (slot == 0) ring[LAT_RING] = v;
+            if (slot < LAT_TAIL) ring[LAT_RING + slot] = v;
         }
     }
 };
@@ -112,7 +113,7 @@ __device__ __forceinline__ void lat_chain(const uint32_t* lut, const uint8_t* sy
         else { const uint32_t e = lut[slot]; f = e >> 18; bias = e & 0x3FFFu; s = (e >> 14) & 15u; }
         const uint64_t x = (uint64_t)f * ((((uint64_t)hi << 32) | lo) >> pb) + bias;
         lo = (uint32_t)x; hi = (uint32_t)(x >> 32);
-        if ((hi | (lo & 0x80000000u)) == 0) { hi = lo; lo = *reinterpret_cast<const uint32_t*>(ringb + kb); kb = (kb + 4) & (LAT_RING * 4 - 1); kw++; }
+        if ((hi | (lo & 0x80000000u)) == 0) { kb &= LAT_RING * 4 - 1; hi = lo; lo = *reinterpret_cast<const uint32_t*>(ringb + kb); kb += 4; kw++; }
         return s;
     };
     uint32_t mk[32];
@@ -121,6 +122,7 @@ __device__ __forceinline__ void lat_chain(const uint32_t* lut, const uint8_t* sy
     // group of 32 symbols; A decodes first.  Forward: A = x0 (even index); backward from an even top: A = x1.
     auto group = [&](uint32_t& alo, uint32_t& ahi, uint32_t& blo, uint32_t& bhi) -> uint32_t {
         uint32_t keep = 0;
+        kb &= LAT_RING * 4 - 1;                       // wrapped once per group; inside it the offset only grows (mirrored tail)
         const uint32_t kb0 = kb;
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
@@ -140,10 +142,10 @@ __device__ __forceinline__ void lat_chain(const uint32_t* lut, const uint8_t* sy
             const uint32_t wb = pa ? c1 : c0;
             ahi = pa ? alo : ahi; alo = pa ? c0 : alo;
             bhi = pq ? blo : bhi; blo = pq ? wb : blo;
-            kb = (kb + (pa ? 4u : 0u) + (pq ? 4u : 0u)) & (LAT_RING * 4 - 1);
+            kb += (pa ? 4u : 0u) + (pq ? 4u : 0u);
             keep |= (ka & mk[j]) | (kbv & mk[j + 1]);
         }
-        kw += ((kb - kb0) & (LAT_RING * 4 - 1)) >> 2;
+        kw += (kb - kb0) >> 2;
         if (kw + LAT_HALF >= loaded) { __syncwarp(); ws.stage(ring, loaded, lane); loaded += LAT_HALF; __syncwarp(); }   // warp-uniform
         return TWO ? keep : ((keep >> 14) & 15u);
     };
