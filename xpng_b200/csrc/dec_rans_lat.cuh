@@ -27,7 +27,8 @@ namespace xpb {
 constexpr uint32_t LAT_RING = 512;               // words; refilled in halves (a group of 32 symbols consumes at most 32)
 constexpr uint32_t LAT_HALF = LAT_RING / 2;
 constexpr uint32_t LAT_TAIL = 36;                // slots 0 .. LAT_TAIL-1 are mirrored behind the ring: a group reads up to 33 words past its start without wrapping
-constexpr uint32_t LAT_RING_WORDS = LAT_RING + LAT_TAIL;
+constexpr uint32_t LAT_KEEP = LAT_RING + LAT_TAIL;   // 32 words behind the tail: the table entries of the current group of 32 symbols
+constexpr uint32_t LAT_RING_WORDS = LAT_RING + LAT_TAIL + 32;
 
 template <int DIR>
 struct WordSrc {
@@ -116,12 +117,11 @@ __device__ __forceinline__ void lat_chain(const uint32_t* lut, const uint8_t* sy
         if ((hi | (lo & 0x80000000u)) == 0) { kb &= LAT_RING * 4 - 1; hi = lo; lo = *reinterpret_cast<const uint32_t*>(ringb + kb); kb += 4; kw++; }
         return s;
     };
-    uint32_t mk[32];
-#pragma unroll
-    for (int j = 0; j < 32; j++) mk[j] = lane == (uint32_t)(DIR > 0 ? j : 31 - j) ? 0xFFFFFFFFu : 0u;
+    // Symbol j of a group is parked in shared memory (one store per symbol, on the load/store pipe) and lane j picks it up at
+    // the end of the group: cheaper than masks in registers, which the compiler re-derives from lane compares (3 ALU ops).
+    uint32_t* kslot = ring + LAT_KEEP;
     // group of 32 symbols; A decodes first.  Forward: A = x0 (even index); backward from an even top: A = x1.
     auto group = [&](uint32_t& alo, uint32_t& ahi, uint32_t& blo, uint32_t& bhi) -> uint32_t {
-        uint32_t keep = 0;
         kb &= LAT_RING * 4 - 1;                       // wrapped once per group; inside it the offset only grows (mirrored tail)
         const uint32_t kb0 = kb;
 #pragma unroll
@@ -143,8 +143,11 @@ __device__ __forceinline__ void lat_chain(const uint32_t* lut, const uint8_t* sy
             ahi = pa ? alo : ahi; alo = pa ? c0 : alo;
             bhi = pq ? blo : bhi; blo = pq ? wb : blo;
             kb += (pa ? 4u : 0u) + (pq ? 4u : 0u);
-            keep |= (ka & mk[j]) | (kbv & mk[j + 1]);
+            kslot[DIR > 0 ? j : 31 - j] = ka; kslot[DIR > 0 ? j + 1 : 30 - j] = kbv;
         }
+        __syncwarp();
+        const uint32_t keep = kslot[lane];
+        __syncwarp();
         kw += (kb - kb0) >> 2;
         if (kw + LAT_HALF >= loaded) { __syncwarp(); ws.stage(ring, loaded, lane); loaded += LAT_HALF; __syncwarp(); }   // warp-uniform
         return TWO ? keep : ((keep >> 14) & 15u);
