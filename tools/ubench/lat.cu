@@ -87,21 +87,18 @@ __global__ void k_mulhi_par(uint32_t* out, long long* cyc, unsigned long long a)
 // same with add.cc chains written out
 __device__ __forceinline__ unsigned long long mulhi_ptx(unsigned long long x, uint32_t rl, uint32_t rh) {
     const uint32_t xl = (uint32_t)x, xh = (uint32_t)(x >> 32);
-    uint32_t al, ah, bl, bh, ch, dl, dh, lo, hi;
-    asm("{\n\t.reg .u32 cl, m, c1;\n\t"
-        "mul.lo.u32 %0, %9, %10;\n\tmul.hi.u32 %1, %9, %10;\n\t"       // A = xh*rl
-        "mul.lo.u32 %2, %8, %11;\n\tmul.hi.u32 %3, %8, %11;\n\t"       // B = xl*rh
-        "mul.hi.u32 %4, %8, %10;\n\t"                                    // hi(C) = hi(xl*rl)
-        "mul.lo.u32 %5, %9, %11;\n\tmul.hi.u32 %6, %9, %11;\n\t"       // D = xh*rh
-        "add.cc.u32 m, %0, %2;\n\taddc.u32 c1, 0, 0;\n\t"
-        "add.cc.u32 m, m, %4;\n\taddc.u32 c1, c1, 0;\n\t"
-        "add.cc.u32 %5, %5, %1;\n\taddc.u32 %6, %6, 0;\n\t"
-        "add.cc.u32 %3, %3, c1;\n\taddc.u32 c1, 0, 0;\n\t"
-        "add.cc.u32 %5, %5, %3;\n\taddc.u32 %6, %6, c1;\n\t"
-        "mov.u32 %7, 0;\n\t}"
-        : "=&r"(al), "=&r"(ah), "=&r"(bl), "=&r"(bh), "=&r"(ch), "=&r"(dl), "=&r"(dh), "=&r"(lo)
-        : "r"(xl), "r"(xh), "r"(rl), "r"(rh));
-    (void)hi; (void)lo;
+    uint32_t dl, dh;
+    asm("{\n\t.reg .u32 al, ah, bl, bh, ch, m, c1;\n\t"
+        "mul.lo.u32 al, %3, %4;\n\tmul.hi.u32 ah, %3, %4;\n\t"       // A = xh*rl
+        "mul.lo.u32 bl, %2, %5;\n\tmul.hi.u32 bh, %2, %5;\n\t"       // B = xl*rh
+        "mul.hi.u32 ch, %2, %4;\n\t"                                   // hi(C) = hi(xl*rl)
+        "mul.lo.u32 %0, %3, %5;\n\tmul.hi.u32 %1, %3, %5;\n\t"       // D = xh*rh
+        "add.cc.u32 m, al, bl;\n\taddc.u32 c1, 0, 0;\n\t"
+        "add.cc.u32 m, m, ch;\n\taddc.u32 c1, c1, 0;\n\t"
+        "add.cc.u32 %0, %0, ah;\n\taddc.u32 %1, %1, 0;\n\t"
+        "add.cc.u32 bh, bh, c1;\n\taddc.u32 c1, 0, 0;\n\t"
+        "add.cc.u32 %0, %0, bh;\n\taddc.u32 %1, %1, c1;\n\t}"
+        : "=&r"(dl), "=&r"(dh) : "r"(xl), "r"(xh), "r"(rl), "r"(rh));
     return ((unsigned long long)dh << 32) | dl;
 }
 __global__ void k_mulhi_ptx(uint32_t* out, long long* cyc, unsigned long long a) {
