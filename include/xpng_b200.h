@@ -92,6 +92,40 @@ uint32_t xpngb_profile_report(const xpngb_ctx *ctx, char *buf, uint32_t cap);
 /* The CUDA stream (cudaStream_t as void*) the context launches on. */
 void *xpngb_stream(const xpngb_ctx *ctx);
 
+/* ---- Frame batches sharded over the GPUs of one box (host code in C, no NCCL).  The reference's parallel strategy is a
+ * tile cursor plus an ordered concatenation (libxpng.c:146-151, :764-769; offset chain :982); frames are independent, so a
+ * batch is cut into contiguous shards, every shard is coded on its own device with no data-path exchange, and the one
+ * exchange is the table of compressed sizes, from which every participant derives the same offsets. */
+
+/* Frame i of n belongs to shard floor(i * nshards / n); shard k owns [first, first + count). */
+void xpngb_shard_range(uint32_t n, uint32_t nshards, uint32_t shard, uint32_t *first, uint32_t *count);
+/* Exclusive scan of 16-byte padded sizes: where file i starts when the n files are written back to back. */
+void xpngb_packed_offsets(const uint64_t *sizes, uint32_t n, uint64_t *offsets, uint64_t *total);
+
+/* One process: a pool holds one codec context per device and drives each from its own host thread. */
+typedef struct xpngb_pool xpngb_pool;
+int xpngb_pool_create(xpngb_pool **pool, const int *devices /* NULL: 0..ndev-1 */, uint32_t ndev);
+void xpngb_pool_destroy(xpngb_pool *pool);
+uint32_t xpngb_pool_size(const xpngb_pool *pool);
+xpngb_ctx *xpngb_pool_context(const xpngb_pool *pool, uint32_t k);
+const char *xpngb_pool_last_error(const xpngb_pool *pool);
+/* xpngb_encode / xpngb_decode of n images in HOST memory, shard k on pool device k.  Encode: `out` must hold
+ * xpngb_encode_bound(imgs, n) bytes; shard k writes its files into its own slice of `out`, out_offsets[i] is the
+ * position of file i inside `out`, and the files are byte-identical to a one-device call. */
+int xpngb_pool_encode(xpngb_pool *pool, int level, xpngb_image *imgs, uint32_t n, const void *pixels, uint64_t pixels_size,
+                      void *out, uint64_t out_cap, uint64_t *out_offsets, uint64_t *out_sizes);
+int xpngb_pool_decode(xpngb_pool *pool, xpngb_image *imgs, uint32_t n, const void *files, uint64_t files_size,
+                      const uint64_t *file_offsets, const uint64_t *file_sizes, void *pixels, uint64_t pixels_cap);
+
+/* One process per device (torchrun-style launch): the size tables of the ranks meet in a POSIX shared-memory segment.
+ * `name` must be the same on every rank and unique per job (e.g. the rendezvous port); rank 0 creates the segment. */
+typedef struct xpngb_gather xpngb_gather;
+int xpngb_gather_open(xpngb_gather **g, const char *name, uint32_t rank, uint32_t world, uint32_t max_items);
+/* Collective: rank r passes the sizes of its shard (xpngb_shard_range(n, world, r)); every rank receives all n sizes and
+ * the packed offsets derived from them. */
+int xpngb_gather_sizes(xpngb_gather *g, uint32_t n, const uint64_t *local_sizes, uint64_t *all_sizes, uint64_t *all_offsets);
+void xpngb_gather_close(xpngb_gather *g);
+
 /* Reversible YCoCg-R lifting of n RGB triples on the device (Tell_Me_Why/YCoCg-R.c:22,:31): a side
  * component, NOT part of the .xpng bit stream.  rgb: 3*n bytes; ycc: 3*n int16 (Y, Co, Cg). */
 int xpngb_ycocg_forward(xpngb_ctx *ctx, const uint8_t *rgb_host, int16_t *ycc_host, uint64_t n);

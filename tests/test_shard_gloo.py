@@ -1,5 +1,6 @@
-"""N > 1 host logic on CPU: two gloo ranks shard a frame batch, code their shards (with the oracle standing in for
-the GPU codec, which does not exist in this container) and agree on the global size/offset table."""
+"""N > 1 host logic on CPU: two ranks (launched and fenced with gloo) shard a frame batch, code their shards (with the
+oracle standing in for the GPU codec, which does not exist in this container) and agree on the global size/offset
+table through the C shared-memory gather of include/xpng_b200.h (xpngb_gather_*)."""
 import os
 import socket
 
@@ -24,9 +25,14 @@ def _worker(rank, world, port, n, level, out):
         frames = _frames(n)
         lo, hi = shard.shard_range(n, rank, world)
         files = [po.encode(level, f) for f in frames[lo:hi]]
-        offsets, sizes = shard.global_table([len(f) for f in files], n)
+        # the size/offset gather is the C one (shared memory, no torch.distributed): gloo is only the launcher's barrier here
+        g = shard.Gather(f"test{port}", rank, world, max(n, 1))
+        offsets, sizes = g.sizes(n, [len(f) for f in files])
+        offsets2, sizes2 = g.sizes(n, [len(f) + 1 for f in files])     # a second round through the other half of the segment
+        assert sizes2 == [s + 1 for s in sizes]
         out.put((rank, lo, hi, offsets, sizes, [bytes(f) for f in files]))
         dist.barrier()
+        g.close()
     finally:
         dist.destroy_process_group()
 

@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import xpng_b200
 from xpng_b200 import synth, Codec
 nf = int(sys.argv[1])
-imgs = [synth.sintel_like(1000 + i) for i in range(nf)]
+imgs = synth.sintel_batch(range(1000, 1000 + nf))
 lib = xpng_b200.lib()
 shapes = [a.shape for a in imgs]
 descs, total = Codec.layout(shapes)

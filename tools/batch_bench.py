@@ -37,6 +37,6 @@ def run(name, imgs, levels, reps=3):
 if __name__ == "__main__":
     nf = int(sys.argv[1]) if len(sys.argv) > 1 else 64
     which = sys.argv[2] if len(sys.argv) > 2 else "345"
-    if "3" in which: run(f"cfg3 1080p sintel-like x{nf}", [synth.sintel_like(1000 + i) for i in range(nf)], (1, 2))
+    if "3" in which: run(f"cfg3 1080p sintel-like x{nf}", synth.sintel_batch(range(1000, 1000 + nf)), (1, 2))
     if "5" in which: run("cfg5 gray 4096^2 x4", [synth.gray_as_rgb(4096, 4096, 3000 + i) for i in range(4)], (2, 1))
     if "4" in which: run("cfg4 rgba 8192^2", [synth.rgba(8192, 8192, 2)], (1,))

@@ -7,7 +7,7 @@ import xpng_b200
 from xpng_b200 import synth, Codec
 nf = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 levels = [int(c) for c in (sys.argv[2] if len(sys.argv) > 2 else "1")]
-imgs = [synth.sintel_like(1000 + i) for i in range(nf)]
+imgs = synth.sintel_batch(range(1000, 1000 + nf))
 cd = Codec(0); lib = xpng_b200.lib()
 shapes = [a.shape for a in imgs]
 descs, total = Codec.layout(shapes)

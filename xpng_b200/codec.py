@@ -63,6 +63,22 @@ def lib():
         L.xpngb_profile_report.restype = u32; L.xpngb_profile_report.argtypes = [vp, C.c_char_p, u32]
         L.xpngb_ycocg_forward.restype = C.c_int; L.xpngb_ycocg_forward.argtypes = [vp, vp, vp, u64]
         L.xpngb_ycocg_inverse.restype = C.c_int; L.xpngb_ycocg_inverse.argtypes = [vp, vp, vp, u64]
+        # frame batches sharded over devices / ranks (host C, no NCCL): include/xpng_b200.h
+        L.xpngb_shard_range.restype = None; L.xpngb_shard_range.argtypes = [u32, u32, u32, C.POINTER(u32), C.POINTER(u32)]
+        L.xpngb_packed_offsets.restype = None
+        L.xpngb_packed_offsets.argtypes = [C.POINTER(u64), u32, C.POINTER(u64), C.POINTER(u64)]
+        L.xpngb_pool_create.restype = C.c_int; L.xpngb_pool_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), u32]
+        L.xpngb_pool_destroy.restype = None; L.xpngb_pool_destroy.argtypes = [vp]
+        L.xpngb_pool_size.restype = u32; L.xpngb_pool_size.argtypes = [vp]
+        L.xpngb_pool_last_error.restype = C.c_char_p; L.xpngb_pool_last_error.argtypes = [vp]
+        L.xpngb_pool_encode.restype = C.c_int
+        L.xpngb_pool_encode.argtypes = [vp, C.c_int, C.POINTER(_Image), u32, vp, u64, vp, u64, C.POINTER(u64), C.POINTER(u64)]
+        L.xpngb_pool_decode.restype = C.c_int
+        L.xpngb_pool_decode.argtypes = [vp, C.POINTER(_Image), u32, vp, u64, C.POINTER(u64), C.POINTER(u64), vp, u64]
+        L.xpngb_gather_open.restype = C.c_int; L.xpngb_gather_open.argtypes = [C.POINTER(vp), C.c_char_p, u32, u32, u32]
+        L.xpngb_gather_sizes.restype = C.c_int
+        L.xpngb_gather_sizes.argtypes = [vp, u32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64)]
+        L.xpngb_gather_close.restype = None; L.xpngb_gather_close.argtypes = [vp]
         for name in ("xpng_store", "xpng_load", "xpng_from_jpg", "xpng_store_T", "xpng_load_T", "xpng_from_jpg_T", "store_7", "load_7"):
             getattr(L, name).restype = C.c_bool
         L.xpng_store.argtypes = [u64, C.POINTER(_Xpng), C.c_char_p]

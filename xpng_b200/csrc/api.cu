@@ -1,6 +1,13 @@
 // api.cu — host orchestration and the C ABI (include/xpng_b200.h) of the B200 xPNG codec.
-// Everything here is plumbing: tile tables (libxpng.c:51-83), scratch layout, kernel launches on one
-// stream, host<->device copies.  All codec arithmetic lives in the kernels.
+// Everything here is plumbing: tile tables (libxpng.c:51-83), scratch layout, kernel launches, host<->device
+// copies.  All codec arithmetic lives in the kernels.
+//
+// Execution model.  A context owns LANES: a lane is a set of CUDA streams plus its own scratch buffers.  A call
+// cuts its batch into chunks of whole images and issues every chunk on its own lane WITHOUT waiting for it; only at
+// the end does the host collect the per-chunk size tables (encode) or error flags (decode).  The serial chains of the
+// bit stream (rANS recurrences, context walk) leave most of the machine idle while they run; with several chunks
+// in flight the data-parallel kernels of one chunk fill the SMs under the chains of another, and with host buffers the
+// H2D / D2H copies of one chunk overlap the kernels of its neighbours.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -11,12 +18,15 @@
 #include "../../include/xpng_b200.h"
 #include "common.cuh"
 #include "enc_front.cuh"
+#include "enc_front2.cuh"
 #include "enc_back.cuh"
 #include "enc_m2.cuh"
 #include "enc_rans_lat.cuh"
 #include "dec_m1.cuh"
 #include "dec_back.cuh"
 #include "dec_rans_lat.cuh"
+#include "dec_rans_pair.cuh"
+#include "dec_walk3.cuh"
 #include "misc.cuh"
 #include "orient.cuh"
 
@@ -27,25 +37,31 @@ struct PinBuf { void* p = nullptr; size_t cap = 0; };
 
 struct xpngb_ctx {
     int device = 0;
+    xpngb_ctx* root = nullptr;                 // the context the caller holds: error text, launch counter, profile table, tunables
+    std::vector<xpngb_ctx*> lanes;             // root only: further lanes (lane 0 is the root itself), created on demand
     static constexpr int NSIDE = 5;
     cudaStream_t stream = nullptr, side[NSIDE] = {}, cur = nullptr;   // main stream, side streams for independent chains, stream of the next launch
     cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, pe0 = nullptr, pe1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, pe0 = nullptr, pe1 = nullptr, ev_done = nullptr;
     int profile = 0;   // 1: per-kernel CUDA-event timing accumulated (serialises the launches); 2: also print to stderr
     struct ProfRow { const char* name; double ms; uint32_t count; };
     std::vector<ProfRow> prof;
     char err[512] = { 0 };
     float last_ms = 0.f;
     uint32_t launches = 0;
-    uint64_t max_chunk_px = 1ull << 30;
+    uint64_t max_chunk_px = 1ull << 30;       // XPNGB_CHUNK_MPIX: upper bound of a chunk (bounds the scratch of a lane)
+    uint32_t pipe_lanes = 8;                  // XPNGB_PIPE_LANES: chunks in flight per call
+    uint64_t pipe_min_px = 32ull << 20;       // XPNGB_PIPE_MIN_MPIX: no chunk smaller than this
+    bool front_v1 = false;                    // XPNGB_FRONT=1: first-generation front end for RGB tiles too (A/B, tests)
     bool walk_global = false, walk_ring = false;   // XPNGB_WALK=global | ring: force a walk variant (tests, A/B)
     uint32_t direct_max_tiles = 148;  // level-2 decode: tiles per call up to which the 64 KiB direct tables are used (3 chains per SM stay resident)
     uint32_t v2_direct_max_tiles = ~0u;  // level-1 decode: same trade for the 16 KiB context tables
-    uint32_t lat_max_blocks = 32768;  // entropy blocks per launch up to which the warp-per-block (latency) kernels are used (measured crossover, profiles/)
+    uint32_t unr_multi_max_tiles = 592, unr_force = 0;   // un-predict: tiles per call up to which a tile gets 8 warps; XPNGB_UNR_NW forces a variant (A/B)
+    uint32_t lat_max_blocks = 32768;  // entropy blocks per call up to which the warp-per-block (latency) kernels are used (measured crossover, profiles/)
     // device scratch
     DevBuf pixels, norm, files, arena, tiles, imgs, seg_tile, costs, hist, seginfo, place, vplace, vcnt, sym_area,
         bits_area, alpha, streams, blocks, state, outs, flags, skip, dimgs, dtiles, plane, nlseq, rowcnt, rowbits,
-        rows, edge, errflag, hdr, offs, m2a, m2b, tclass, tabs, ccnt, cbit, resv, oriented, odesc;
+        rows, edge, errflag, hdr, offs, m2a, m2b, tclass, tabs, ccnt, cbit, resv, oriented, odesc, pdw;
     PinBuf pin_a, pin_b, pin_o;   // pin_o: orientation descriptors (their upload may still be in flight when an encode reuses pin_a)
 };
 
@@ -53,26 +69,27 @@ struct xpngb_ctx {
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
         if (e_ != cudaSuccess) {                                                                   \
-            snprintf(ctx->err, sizeof ctx->err, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            snprintf(ctx->root->err, sizeof ctx->root->err, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
             return 1;                                                                              \
         }                                                                                          \
     } while (0)
-#define FAIL(...)                                                \
-    do {                                                         \
-        snprintf(ctx->err, sizeof ctx->err, __VA_ARGS__);        \
-        return 1;                                                \
+#define FAIL(...)                                                            \
+    do {                                                                     \
+        snprintf(ctx->root->err, sizeof ctx->root->err, __VA_ARGS__);        \
+        return 1;                                                            \
     } while (0)
 #define LAUNCH(kernel, grid, block, smem, ...)                                                      \
     do {                                                                                            \
-        if (ctx->profile) cudaEventRecord(ctx->pe0, ctx->cur);                                      \
+        xpngb_ctx* r_ = ctx->root;                                                                  \
+        if (r_->profile) cudaEventRecord(ctx->pe0, ctx->cur);                                       \
         kernel<<<grid, block, smem, ctx->cur>>>(__VA_ARGS__);                                       \
-        ctx->launches++;                                                                            \
+        r_->launches++;                                                                             \
         CK(cudaGetLastError());                                                                     \
-        if (ctx->profile) {                                                                         \
+        if (r_->profile) {                                                                          \
             float ms_ = 0; cudaEventRecord(ctx->pe1, ctx->cur); cudaEventSynchronize(ctx->pe1);     \
             cudaEventElapsedTime(&ms_, ctx->pe0, ctx->pe1);                                         \
-            prof_add(ctx, #kernel, ms_);                                                            \
-            if (ctx->profile > 1) fprintf(stderr, "[xpngb] %-28s %9.3f ms\n", #kernel, ms_);       \
+            prof_add(r_, #kernel, ms_);                                                             \
+            if (r_->profile > 1) fprintf(stderr, "[xpngb] %-28s %9.3f ms\n", #kernel, ms_);       \
         }                                                                                           \
     } while (0)
 
@@ -193,7 +210,7 @@ static void m2_set_attributes() {
 }
 
 // classification, RGB front end (contexts + value streams), grey candidates, backward rANS, size decisions
-static int m2_encode_tiles(xpngb_ctx* ctx, const Plan& P, uint32_t ntiles, uint32_t nseg) {
+static int m2_encode_tiles(xpngb_ctx* ctx, const Plan& P, uint32_t ntiles, uint32_t nseg, bool lat) {
     const TileDesc* d_tiles = (const TileDesc*)ctx->tiles.p;
     const uint32_t* d_seg_tile = (const uint32_t*)ctx->seg_tile.p;
     ENSURE(tclass, ntiles); ENSURE(skip, ntiles); ENSURE(tabs, (size_t)ntiles * 17 * TAB_WORDS * 4);
@@ -202,8 +219,9 @@ static int m2_encode_tiles(xpngb_ctx* ctx, const Plan& P, uint32_t ntiles, uint3
     LAUNCH(k_m2_classify, ntiles, 256, 0, d_tiles, (const ImageDesc*)ctx->imgs.p, (uint8_t*)ctx->tclass.p);
     LAUNCH(k_m2_skipmask, (ntiles + 255) / 256, 256, 0, (const uint8_t*)ctx->tclass.p, (uint8_t*)ctx->skip.p, ntiles);
     FrontArgs fa{ d_tiles, d_seg_tile, nullptr, (const uint32_t*)ctx->costs.p, (const uint8_t*)ctx->skip.p, (SegInfo*)ctx->seginfo.p,
-                  (uint8_t*)ctx->sym_area.p, (uint8_t*)ctx->bits_area.p, nullptr, (uint32_t*)ctx->hist.p, (uint16_t*)ctx->vcnt.p };
-    LAUNCH(k_front<2>, nseg, FRONT_THREADS, 0, fa);
+                  (uint8_t*)ctx->sym_area.p, (uint8_t*)ctx->bits_area.p, nullptr, (uint32_t*)ctx->hist.p, (uint16_t*)ctx->vcnt.p, 0u };
+    if (ctx->root->front_v1) LAUNCH(k_front<2>, nseg, FRONT_THREADS, 0, fa);
+    else LAUNCH(k_front2<2>, nseg, FRONT_THREADS, 0, fa);      // level 2 codes RGB tiles only
     TileScanArgs ta{ d_tiles, (const SegInfo*)ctx->seginfo.p, (const uint32_t*)ctx->costs.p, (const uint16_t*)ctx->vcnt.p,
                      (SegPlace*)ctx->place.p, (SegPlace*)ctx->vplace.p, (uint32_t*)ctx->hist.p, (TileState*)ctx->state.p,
                      (const uint8_t*)ctx->skip.p, ntiles };
@@ -215,7 +233,7 @@ static int m2_encode_tiles(xpngb_ctx* ctx, const Plan& P, uint32_t ntiles, uint3
     LAUNCH(k_m2_grey_front, nseg, 256, 0, d_tiles, d_seg_tile, (const uint8_t*)ctx->tclass.p, (uint8_t*)ctx->streams.p, (uint32_t*)ctx->hist.p);
     RansV1Args ra{ d_tiles, (TileState*)ctx->state.p, (const uint32_t*)ctx->hist.p, (const uint8_t*)ctx->tclass.p,
                    (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->blocks.p, (uint32_t*)ctx->tabs.p, ntiles, 0, 17, 0, 0 };
-    if (17 * ntiles <= ctx->lat_max_blocks * 5 / 2) {   // level 2 crosses over later than level 1 (profiles/: ~600 vs ~380 frames of 1080p)
+    if (lat) {
         auto k_rans_v1_pair_16 = k_rans_v1_pair<16>; auto k_rans_v1_pair_256 = k_rans_v1_pair<256>;
         // alphabets above 16 symbols and the grey candidates go to a side stream that forks BEFORE the main launch but is
         // fed AFTER it: the small-alphabet kernel holds the longest chains, and in a batch its CTAs must be placed first
@@ -249,61 +267,94 @@ static int m2_assemble(xpngb_ctx* ctx, const AssembleArgs& aa, uint32_t ntiles) 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Context
+// Context and lanes
 // ------------------------------------------------------------------------------------------------
+static void lane_free(xpngb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int k = 0; k < xpngb_ctx::NSIDE; k++) if (ctx->side[k]) cudaStreamSynchronize(ctx->side[k]);
+    DevBuf* all[] = { &ctx->pixels, &ctx->norm, &ctx->files, &ctx->arena, &ctx->tiles, &ctx->imgs, &ctx->seg_tile, &ctx->costs,
+                      &ctx->hist, &ctx->seginfo, &ctx->place, &ctx->vplace, &ctx->vcnt, &ctx->sym_area, &ctx->bits_area, &ctx->alpha,
+                      &ctx->streams, &ctx->blocks, &ctx->state, &ctx->outs, &ctx->flags, &ctx->skip, &ctx->dimgs, &ctx->dtiles,
+                      &ctx->plane, &ctx->nlseq, &ctx->rowcnt, &ctx->rowbits, &ctx->rows, &ctx->edge, &ctx->errflag, &ctx->hdr,
+                      &ctx->offs, &ctx->m2a, &ctx->m2b, &ctx->tclass, &ctx->tabs, &ctx->ccnt, &ctx->cbit, &ctx->resv, &ctx->oriented,
+                      &ctx->odesc, &ctx->pdw };
+    for (DevBuf* b : all) if (b->p) cudaFree(b->p);
+    if (ctx->pin_a.p) cudaFreeHost(ctx->pin_a.p);
+    if (ctx->pin_b.p) cudaFreeHost(ctx->pin_b.p);
+    if (ctx->pin_o.p) cudaFreeHost(ctx->pin_o.p);
+    cudaEvent_t evs[] = { ctx->ev0, ctx->ev1, ctx->ev_fork, ctx->pe0, ctx->pe1, ctx->ev_done };
+    for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
+    for (int k = 0; k < xpngb_ctx::NSIDE; k++) { if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]); if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]); }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+// A lane: streams, events and (empty, grow-only) scratch.  root == nullptr creates the root lane.
+static xpngb_ctx* lane_new(int device, xpngb_ctx* root) {
+    xpngb_ctx* ctx = new xpngb_ctx();
+    ctx->device = device; ctx->root = root ? root : ctx;
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
+              cudaEventCreate(&ctx->pe0) == cudaSuccess && cudaEventCreate(&ctx->pe1) == cudaSuccess;
+    for (int k = 0; ok && k < xpngb_ctx::NSIDE; k++)
+        ok = cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { lane_free(ctx); return nullptr; }
+    ctx->cur = ctx->stream;
+    return ctx;
+}
+// Lane i of a context (0 = the root itself).
+static xpngb_ctx* lane_get(xpngb_ctx* root, uint32_t i) {
+    if (i == 0) return root;
+    while (root->lanes.size() < i) {
+        xpngb_ctx* l = lane_new(root->device, root);
+        if (!l) return nullptr;
+        root->lanes.push_back(l);
+    }
+    return root->lanes[i - 1];
+}
+
 extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     if (!out) return 1;
     *out = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return 1;
     if (cudaSetDevice(device) != cudaSuccess) return 1;
-    xpngb_ctx* ctx = new xpngb_ctx();
-    ctx->device = device;
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) { delete ctx; return 1; }
-    for (int k = 0; k < xpngb_ctx::NSIDE; k++)
-        if (cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return 1; }
-    ctx->cur = ctx->stream;
-    cudaEventCreate(&ctx->pe0); cudaEventCreate(&ctx->pe1);
+    xpngb_ctx* ctx = lane_new(device, nullptr);
+    if (!ctx) return 1;
     if (const char* e = getenv("XPNGB_PROFILE")) ctx->profile = atoi(e) ? 2 : 0;
     if (const char* e = getenv("XPNGB_CHUNK_MPIX")) { const long v = atol(e); if (v > 0) ctx->max_chunk_px = (uint64_t)v << 20; }
+    if (const char* e = getenv("XPNGB_PIPE_LANES")) { const long v = atol(e); if (v > 0 && v <= 64) ctx->pipe_lanes = (uint32_t)v; }
+    if (const char* e = getenv("XPNGB_PIPE_MIN_MPIX")) { const long v = atol(e); if (v > 0) ctx->pipe_min_px = (uint64_t)v << 20; }
     { auto k_big = k_rans_v2<256, 32>; cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 16); }
     m2_set_attributes();
     if (const char* e = getenv("XPNGB_LAT_MAX_BLOCKS")) ctx->lat_max_blocks = (uint32_t)atol(e);
     if (const char* e = getenv("XPNGB_V2_DIRECT_MAX_TILES")) ctx->v2_direct_max_tiles = (uint32_t)atol(e);
     if (const char* e = getenv("XPNGB_WALK")) { ctx->walk_global = !strcmp(e, "global"); ctx->walk_ring = !strcmp(e, "ring"); }
     if (const char* e = getenv("XPNGB_DIRECT_MAX_TILES")) ctx->direct_max_tiles = (uint32_t)atol(e);
+    if (const char* e = getenv("XPNGB_UNR_NW")) ctx->unr_force = (uint32_t)atol(e);
+    if (const char* e = getenv("XPNGB_FRONT")) ctx->front_v1 = atoi(e) == 1;
     { auto p = k_rans_v2_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * PAIR_BLK * 24); }
     { auto p = k_rans_v1_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * PAIR_BLK * 24); }
     cudaFuncSetAttribute(k_dec_unpredict_rows<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2 * 32 * UNR_PITCH);
     cudaFuncSetAttribute(k_dec_unpredict_rows<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 32 * UNR_PITCH);
     cudaFuncSetAttribute(k_dec_walk_smem<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (WALK_SMEM_MAX_SYMS / 8 + 32) * 4);
     cudaFuncSetAttribute(k_dec_rans_v1_lat, cudaFuncAttributeMaxDynamicSharedMemorySize, lat_smem(LUT_ONE_14));
+    { auto p = k_dec_rans_pair<1, 0>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_WARPS * PD_BIG_BYTES); }
+    { auto p = k_dec_rans_pair<2, 0>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_WARPS * PD_BIG_BYTES); }
     *out = ctx;
     return 0;
 }
 
 extern "C" void xpngb_destroy(xpngb_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    for (int k = 0; k < xpngb_ctx::NSIDE; k++) cudaStreamSynchronize(ctx->side[k]);
-    DevBuf* all[] = { &ctx->pixels, &ctx->norm, &ctx->files, &ctx->arena, &ctx->tiles, &ctx->imgs, &ctx->seg_tile, &ctx->costs,
-                      &ctx->hist, &ctx->seginfo, &ctx->place, &ctx->vplace, &ctx->vcnt, &ctx->sym_area, &ctx->bits_area, &ctx->alpha,
-                      &ctx->streams, &ctx->blocks, &ctx->state, &ctx->outs, &ctx->flags, &ctx->skip, &ctx->dimgs, &ctx->dtiles,
-                      &ctx->plane, &ctx->nlseq, &ctx->rowcnt, &ctx->rowbits, &ctx->rows, &ctx->edge, &ctx->errflag, &ctx->hdr,
-                      &ctx->offs, &ctx->m2a, &ctx->m2b, &ctx->tclass, &ctx->tabs, &ctx->ccnt, &ctx->cbit, &ctx->resv, &ctx->oriented, &ctx->odesc };
-    for (DevBuf* b : all) if (b->p) cudaFree(b->p);
-    if (ctx->pin_a.p) cudaFreeHost(ctx->pin_a.p);
-    if (ctx->pin_b.p) cudaFreeHost(ctx->pin_b.p);
-    if (ctx->pin_o.p) cudaFreeHost(ctx->pin_o.p);
-    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
-    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->pe0); cudaEventDestroy(ctx->pe1);
-    for (int k = 0; k < xpngb_ctx::NSIDE; k++) { cudaEventDestroy(ctx->ev_join[k]); cudaStreamDestroy(ctx->side[k]); }
-    cudaStreamDestroy(ctx->stream);
-    delete ctx;
+    for (xpngb_ctx* l : ctx->lanes) lane_free(l);
+    ctx->lanes.clear();
+    lane_free(ctx);
 }
 
 extern "C" const char* xpngb_last_error(const xpngb_ctx* ctx) { return ctx ? ctx->err : "no context"; }
@@ -337,32 +388,73 @@ extern "C" int xpngb_peek(const void* file, uint64_t size, xpngb_image* img) {
     return !(img->mode == 1 || img->mode == 2 || img->mode == 7);   // libxpng.c:972
 }
 
+// Cut n images into chunks of whole images: at most pipe_lanes chunks of roughly equal pixel count, none below
+// pipe_min_px (so small calls stay one chunk) and none above max_chunk_px (scratch bound).  Returns the chunk starts + n.
+static std::vector<uint32_t> cut_chunks(const xpngb_ctx* ctx, const xpngb_image* imgs, uint32_t n) {
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; i++) total += imgs[i].w * imgs[i].h;
+    uint64_t want = (total + ctx->pipe_lanes - 1) / ctx->pipe_lanes;
+    if (want < ctx->pipe_min_px) want = ctx->pipe_min_px;
+    if (want > ctx->max_chunk_px) want = ctx->max_chunk_px;
+    std::vector<uint32_t> cuts{ 0 };
+    uint64_t px = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint64_t p = imgs[i].w * imgs[i].h;
+        if (px && px + p > want) { cuts.push_back(i); px = 0; }
+        px += p;
+    }
+    cuts.push_back(n);
+    return cuts;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Encode
 // ------------------------------------------------------------------------------------------------
-static int encode_chunk(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32_t n, const uint8_t* dpix, uint8_t* dout,
-                        uint64_t out_base, uint64_t out_cap, uint64_t* out_offsets, uint64_t* out_sizes, uint64_t* used) {
-    // ---- normalisation / whole-image scans (one sync, only when needed)
+// Whole-image single colour at level 2 (libxpng.c:741-753), decided on the device for RGB batches so that the host
+// never waits for the scan.
+__global__ void k_apply_scan(ImageDesc* imgs, const uint32_t* flags, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && imgs[i].mode == 2 && !(flags[i] & SCAN_NOT_SINGLE)) imgs[i].mode = 2 | 0x100;
+}
+
+// One chunk in flight on a lane: what the host needs to finish it.
+struct EncChunk {
+    xpngb_ctx* lane = nullptr;
+    xpngb_image* imgs = nullptr; uint32_t n = 0;
+    uint64_t* out_offsets = nullptr; uint64_t* out_sizes = nullptr;
+    std::vector<uint32_t> pxsz;
+    uint64_t out_base = 0, out_end = 0;     // region of the device arena: [out_base, out_end) is this chunk's bound, files are packed from out_base
+    bool finished = false; uint64_t used_end = 0;
+};
+
+static int encode_finish(xpngb_ctx* ctx, EncChunk& C);
+
+// Launch everything for one chunk on lane `ctx`; nothing here waits for the device unless the chunk holds RGBA images
+// (alpha normalisation changes the pixel size, which the tile plan depends on).
+static int encode_issue(xpngb_ctx* ctx, int level, bool lat, const uint8_t* dpix, uint8_t* dout, EncChunk& C) {
+    xpngb_image* imgs = C.imgs; const uint32_t n = C.n;
+    ctx->cur = ctx->stream;
     bool any_rgba = false;
     for (uint32_t i = 0; i < n; i++) any_rgba |= imgs[i].A != 0;
-    std::vector<uint32_t> flags(n, 0);
+    std::vector<uint32_t> flags(n, SCAN_NOT_SINGLE);
     std::vector<uint64_t> addr(n);
-    std::vector<uint32_t> pxsz(n);
+    std::vector<uint32_t>& pxsz = C.pxsz; pxsz.resize(n);
     for (uint32_t i = 0; i < n; i++) { addr[i] = (uint64_t)(dpix + imgs[i].offset); pxsz[i] = imgs[i].A ? 4 : 3; }
-    if (any_rgba || level == 2) {
-        Plan S;   // only the image table is used
+    const unsigned scan_chunks = n >= 148 ? 8u : (1184u / n > 592u ? 592u : 1184u / n);   // ~8 CTAs per SM over the whole chunk
+    if (any_rgba) {
+        // ---- normalisation / whole-image scans: the one place where the host waits inside a chunk
+        std::vector<ImageDesc> S(n);
         for (uint32_t i = 0; i < n; i++) {
             ImageDesc I{}; I.px_off = addr[i]; I.w = (uint32_t)imgs[i].w; I.h = (uint32_t)imgs[i].h; I.pxsz = pxsz[i];
             I.raw_size = imgs[i].w * imgs[i].h * pxsz[i];
-            S.imgs.push_back(I);
+            S[i] = I;
         }
         const size_t nb = n * sizeof(ImageDesc);
         ENSURE(imgs, nb); ENSURE(flags, n * 4);
         if (ensure_pin(ctx, ctx->pin_a, nb)) return 1;
-        memcpy(ctx->pin_a.p, S.imgs.data(), nb);
+        memcpy(ctx->pin_a.p, S.data(), nb);
         CK(cudaMemcpyAsync(ctx->imgs.p, ctx->pin_a.p, nb, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemsetAsync(ctx->flags.p, 0, n * 4, ctx->stream));
-        const unsigned scan_chunks = n >= 148 ? 8u : (1184u / n > 592u ? 592u : 1184u / n);   // ~8 CTAs per SM over the whole batch
         LAUNCH(k_image_scan, dim3(scan_chunks, n), 256, 0, (const ImageDesc*)ctx->imgs.p, (uint32_t*)ctx->flags.p);
         CK(cudaMemcpyAsync(flags.data(), ctx->flags.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -385,24 +477,25 @@ static int encode_chunk(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32_t n
             }
         }
     }
-    // ---- effective level per image (libxpng.c:735, :741-755)
+    // ---- effective level per image (libxpng.c:735, :741-755).  Without RGBA images the single-colour test of level 2
+    // is applied on the device (k_apply_scan); the host only needs to know that level-2 work exists.
     std::vector<uint32_t> mode(n);
     bool any1 = false, any2 = false;
     for (uint32_t i = 0; i < n; i++) {
         const uint64_t s = imgs[i].w * imgs[i].h * pxsz[i];
         uint32_t m = (uint32_t)level;
         if (s <= 4) m = 7;
-        if (m == 2 && !(flags[i] & SCAN_NOT_SINGLE)) m = 2 | 0x100;
+        if (m == 2 && any_rgba && !(flags[i] & SCAN_NOT_SINGLE)) m = 2 | 0x100;
         else if (m == 2 && pxsz[i] == 4) m = 1;
         if ((m == 1) && pxsz[i] == 4 && (imgs[i].w < 4 || imgs[i].h < 4))
             FAIL("image %u: RGBA tiles thinner than 4 pixels are not encodable at level 1/2 (the reference crashes here)", i);
         mode[i] = m; any1 |= m == 1; any2 |= m == 2;
     }
     if (any1 && any2) {
-        // level 2 with some images that keep alpha (coded at level 1, libxpng.c:755): the batch is regrouped into the two
+        // level 2 with some images that keep alpha (coded at level 1, libxpng.c:755): the chunk is regrouped into the two
         // families and each family is encoded in ONE pass (files of a family are adjacent in the arena; the offset table,
-        // not the arena order, is the contract)
-        uint64_t base = out_base;
+        // not the arena order, is the contract).  Only chunks with RGBA images get here, and they have waited already.
+        uint64_t base = C.out_base;
         for (int fam = 0; fam < 2; fam++) {
             std::vector<uint32_t> idx;
             for (uint32_t i = 0; i < n; i++) if ((mode[i] == 1) == (fam == 0)) idx.push_back(i);
@@ -410,16 +503,21 @@ static int encode_chunk(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32_t n
             std::vector<xpngb_image> sub(idx.size());
             std::vector<uint64_t> so(idx.size()), ss(idx.size());
             for (size_t k = 0; k < idx.size(); k++) sub[k] = imgs[idx[k]];
-            if (encode_chunk(ctx, fam == 0 ? 1 : 2, sub.data(), (uint32_t)idx.size(), dpix, dout, base, out_cap, so.data(), ss.data(), &base)) return 1;
-            for (size_t k = 0; k < idx.size(); k++) { imgs[idx[k]] = sub[k]; out_offsets[idx[k]] = so[k]; out_sizes[idx[k]] = ss[k]; }
+            EncChunk S; S.lane = ctx; S.imgs = sub.data(); S.n = (uint32_t)idx.size(); S.out_offsets = so.data(); S.out_sizes = ss.data();
+            S.out_base = base; S.out_end = C.out_end;
+            if (encode_issue(ctx, fam == 0 ? 1 : 2, lat, dpix, dout, S) || encode_finish(ctx, S)) return 1;
+            base = S.used_end;
+            for (size_t k = 0; k < idx.size(); k++) { imgs[idx[k]] = sub[k]; C.out_offsets[idx[k]] = so[k]; C.out_sizes[idx[k]] = ss[k]; }
         }
-        *used = base;
+        C.finished = true; C.used_end = base;
+        CK(cudaEventRecord(ctx->ev_done, ctx->stream));
         return 0;
     }
     // ---- plan
     Plan P;
     const int sfac = any2 ? 4 : 1, bfac = any2 ? 8 : 4;
     for (uint32_t i = 0; i < n; i++) plan_image(P, addr[i], imgs[i].w, imgs[i].h, pxsz[i], mode[i], sfac, bfac);
+    if (P.tiles.size() > (1u << 24) || P.seg_tile.size() > (1u << 28)) FAIL("too many tiles for one chunk (%zu)", P.tiles.size());
     const uint32_t ntiles = (uint32_t)P.tiles.size(), nseg = (uint32_t)P.seg_tile.size();
     if (upload_plan(ctx, P)) return 1;
     ENSURE(outs, n * sizeof(ImageOut)); ENSURE(state, ntiles * sizeof(TileState));
@@ -427,6 +525,12 @@ static int encode_chunk(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32_t n
     const TileDesc* d_tiles = (const TileDesc*)ctx->tiles.p;
     const ImageDesc* d_imgs = (const ImageDesc*)ctx->imgs.p;
     const uint32_t* d_seg_tile = (const uint32_t*)ctx->seg_tile.p;
+    if (any2 && !any_rgba) {
+        ENSURE(flags, n * 4);
+        CK(cudaMemsetAsync(ctx->flags.p, 0, n * 4, ctx->stream));
+        LAUNCH(k_image_scan, dim3(scan_chunks, n), 256, 0, d_imgs, (uint32_t*)ctx->flags.p);
+        LAUNCH(k_apply_scan, (n + 127) / 128, 128, 0, (ImageDesc*)ctx->imgs.p, (const uint32_t*)ctx->flags.p, n);
+    }
 
     if (any1 || any2) {
         const int hstride = any2 ? HIST_STRIDE_M2 : HIST_STRIDE_M1;
@@ -440,8 +544,15 @@ static int encode_chunk(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32_t n
     }
     if (any1) {
         FrontArgs fa{ d_tiles, d_seg_tile, nullptr, (const uint32_t*)ctx->costs.p, nullptr, (SegInfo*)ctx->seginfo.p,
-                      (uint8_t*)ctx->sym_area.p, (uint8_t*)ctx->bits_area.p, (uint8_t*)ctx->alpha.p, (uint32_t*)ctx->hist.p, nullptr };
-        LAUNCH(k_front<1>, nseg, FRONT_THREADS, 0, fa);
+                      (uint8_t*)ctx->sym_area.p, (uint8_t*)ctx->bits_area.p, (uint8_t*)ctx->alpha.p, (uint32_t*)ctx->hist.p, nullptr, 0u };
+        if (ctx->root->front_v1) LAUNCH(k_front<1>, nseg, FRONT_THREADS, 0, fa);
+        else {
+            bool any_rgb = false;
+            for (uint32_t i = 0; i < n; i++) any_rgb |= pxsz[i] == 3 && mode[i] == 1;
+            if (any_rgb) LAUNCH(k_front2<1>, nseg, FRONT_THREADS, 0, fa);
+            fa.rgba_only = 1;
+            if (P.any_rgba) LAUNCH(k_front<1>, nseg, FRONT_THREADS, 0, fa);
+        }
         TileScanArgs ta{ d_tiles, (const SegInfo*)ctx->seginfo.p, (const uint32_t*)ctx->costs.p, nullptr, (SegPlace*)ctx->place.p, nullptr,
                          (uint32_t*)ctx->hist.p, (TileState*)ctx->state.p, nullptr, ntiles };
         LAUNCH(k_tile_scan<1>, (ntiles + 3) / 4, 128, 0, ta);
@@ -451,7 +562,7 @@ static int encode_chunk(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32_t n
         LAUNCH(k_compact<1>, nseg, 256, 0, ca);
         RansV2Args ra{ d_tiles, (TileState*)ctx->state.p, (uint32_t*)ctx->hist.p, (const uint8_t*)ctx->streams.p,
                        (const uint8_t*)ctx->alpha.p, (uint8_t*)ctx->blocks.p, ntiles, 0, 9 };
-        if (9 * ntiles <= ctx->lat_max_blocks) {
+        if (lat) {
             auto k_rans_v2_pair_16 = k_rans_v2_pair<16>; auto k_rans_v2_pair_256 = k_rans_v2_pair<256>;
             if (P.any_rgba) {                          // the alpha blocks are independent of the context blocks: side stream
                 FORK_SIDE(0);                          // forks before, is fed after the main launch (see m2_encode_tiles)
@@ -465,19 +576,19 @@ static int encode_chunk(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32_t n
                 JOIN_SIDE(0);
             }
         } else {
-        auto k_rans_v2_lane_9 = k_rans_v2<9, 128>; auto k_rans_v2_lane_256 = k_rans_v2<256, 32>;
-        LAUNCH(k_rans_v2_lane_9, (9 * ntiles + 127) / 128, 128, 9 * 128 * 16, ra);
-        if (P.any_rgba) {
-            ra.c0 = 9; ra.nc = 1;
-            LAUNCH(k_rans_v2_lane_256, (ntiles + 31) / 32, 32, 256 * 32 * 16, ra);
-        }
+            auto k_rans_v2_lane_9 = k_rans_v2<9, 128>; auto k_rans_v2_lane_256 = k_rans_v2<256, 32>;
+            LAUNCH(k_rans_v2_lane_9, (9 * ntiles + 127) / 128, 128, 9 * 128 * 16, ra);
+            if (P.any_rgba) {
+                ra.c0 = 9; ra.nc = 1;
+                LAUNCH(k_rans_v2_lane_256, (ntiles + 31) / 32, 32, 256 * 32 * 16, ra);
+            }
         }
     }
     if (any2) {
-        if (m2_encode_tiles(ctx, P, ntiles, nseg)) return 1;
+        if (m2_encode_tiles(ctx, P, ntiles, nseg, lat)) return 1;
     }
     LAUNCH(k_image_sizes, (n + 127) / 128, 128, 0, d_imgs, d_tiles, (TileState*)ctx->state.p, (ImageOut*)ctx->outs.p, n);
-    LAUNCH(k_image_offsets, 1, 1, 0, (ImageOut*)ctx->outs.p, n, out_base);
+    LAUNCH(k_image_offsets, 1, 1, 0, (ImageOut*)ctx->outs.p, n, C.out_base);
     {
         AssembleArgs aa{ d_imgs, d_tiles, (const TileState*)ctx->state.p, (const ImageOut*)ctx->outs.p, (const SegInfo*)ctx->seginfo.p,
                          (const SegPlace*)ctx->place.p, nullptr, (const uint8_t*)ctx->bits_area.p, (const uint8_t*)ctx->blocks.p, dout };
@@ -486,16 +597,23 @@ static int encode_chunk(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32_t n
     }
     if (ensure_pin(ctx, ctx->pin_b, n * sizeof(ImageOut))) return 1;
     CK(cudaMemcpyAsync(ctx->pin_b.p, ctx->outs.p, n * sizeof(ImageOut), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventRecord(ctx->ev_done, ctx->stream));
+    return 0;
+}
+
+// Wait for the chunk's size table and hand the results to the caller's arrays.
+static int encode_finish(xpngb_ctx* ctx, EncChunk& C) {
+    CK(cudaEventSynchronize(ctx->ev_done));
+    if (C.finished) return 0;
     const ImageOut* ho = (const ImageOut*)ctx->pin_b.p;
-    uint64_t end = out_base;
-    for (uint32_t i = 0; i < n; i++) {
-        out_offsets[i] = ho[i].off; out_sizes[i] = ho[i].size;
-        imgs[i].A = pxsz[i] == 4; imgs[i].mode = ho[i].mode & 0xFF;
+    uint64_t end = C.out_base;
+    for (uint32_t i = 0; i < C.n; i++) {
+        C.out_offsets[i] = ho[i].off; C.out_sizes[i] = ho[i].size;
+        C.imgs[i].A = C.pxsz[i] == 4; C.imgs[i].mode = ho[i].mode & 0xFF;
         end = ho[i].off + ((ho[i].size + 15) & ~15ull);
     }
-    if (end > out_cap) FAIL("output buffer too small: need %llu bytes, have %llu", (unsigned long long)end, (unsigned long long)out_cap);
-    *used = end;
+    if (end > C.out_end) FAIL("output region too small: need %llu bytes, have %llu", (unsigned long long)(end - C.out_base), (unsigned long long)(C.out_end - C.out_base));
+    C.finished = true; C.used_end = end;
     return 0;
 }
 
@@ -511,59 +629,103 @@ extern "C" int xpngb_encode(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32
         const xpngb_image& m = imgs[i];
         if (!m.w || !m.h || m.w > (1u << 24) || m.h > (1u << 24)) FAIL("image %u: bad dimensions", i);   // libxpng.c:729-730
         if (m.offset & 15) FAIL("image %u: pixel offset must be a multiple of 16", i);
-        if (m.offset + m.w * m.h * (3 + (m.A ? 1 : 0)) > pixels_size) FAIL("image %u: pixels exceed the buffer", i);
+        const uint64_t bytes = m.w * m.h * (3 + (m.A ? 1 : 0));   // w, h <= 2^24: no overflow
+        if (bytes > pixels_size || m.offset > pixels_size - bytes) FAIL("image %u: pixels exceed the buffer", i);
     }
     CK(cudaSetDevice(ctx->device));
     const uint64_t bound = xpngb_encode_bound(imgs, n);
     if (out_on_device && out_cap < bound) FAIL("device output buffer must hold xpngb_encode_bound() = %llu bytes", (unsigned long long)bound);
     const uint8_t* dpix = (const uint8_t*)pixels;
-    if (!pixels_on_device) {
-        ENSURE(pixels, pixels_size);
-        CK(cudaMemcpyAsync(ctx->pixels.p, pixels, pixels_size, cudaMemcpyHostToDevice, ctx->stream));
-        dpix = (const uint8_t*)ctx->pixels.p;
-    }
+    if (!pixels_on_device) { ENSURE(pixels, pixels_size); dpix = (const uint8_t*)ctx->pixels.p; }
     uint8_t* dout = (uint8_t*)out;
     if (!out_on_device) { ENSURE(arena, bound); dout = (uint8_t*)ctx->arena.p; }
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    uint64_t used = 0;
-    if (level == 7) {
-        // stored files need no tiles: header + copy (normalisation still applies to RGBA inputs)
-        bool any_rgba = false;
-        for (uint32_t i = 0; i < n; i++) any_rgba |= imgs[i].A != 0;
-        if (!any_rgba) {
-            std::vector<ImageDesc> I(n); std::vector<uint64_t> offs(n);
-            for (uint32_t i = 0; i < n; i++) {
-                I[i] = ImageDesc{}; I[i].px_off = (uint64_t)(dpix + imgs[i].offset); I[i].w = (uint32_t)imgs[i].w; I[i].h = (uint32_t)imgs[i].h;
-                I[i].pxsz = 3; I[i].raw_size = imgs[i].w * imgs[i].h * 3;
-                offs[i] = used; out_offsets[i] = used; out_sizes[i] = 8 + I[i].raw_size; used += (out_sizes[i] + 15) & ~15ull;
-                imgs[i].mode = 7;
+    bool any_rgba = false;
+    for (uint32_t i = 0; i < n; i++) any_rgba |= imgs[i].A != 0;
+    if (level == 7 && !any_rgba) {
+        // stored files need no tiles: header + copy
+        if (!pixels_on_device) CK(cudaMemcpyAsync(ctx->pixels.p, pixels, pixels_size, cudaMemcpyHostToDevice, ctx->stream));
+        uint64_t used = 0;
+        std::vector<ImageDesc> I(n); std::vector<uint64_t> offs(n);
+        for (uint32_t i = 0; i < n; i++) {
+            I[i] = ImageDesc{}; I[i].px_off = (uint64_t)(dpix + imgs[i].offset); I[i].w = (uint32_t)imgs[i].w; I[i].h = (uint32_t)imgs[i].h;
+            I[i].pxsz = 3; I[i].raw_size = imgs[i].w * imgs[i].h * 3;
+            offs[i] = used; out_offsets[i] = used; out_sizes[i] = 8 + I[i].raw_size; used += (out_sizes[i] + 15) & ~15ull;
+            imgs[i].mode = 7;
+        }
+        ENSURE(imgs, n * sizeof(ImageDesc)); ENSURE(offs, n * 8);
+        if (ensure_pin(ctx, ctx->pin_a, n * (sizeof(ImageDesc) + 8))) return 1;
+        memcpy(ctx->pin_a.p, I.data(), n * sizeof(ImageDesc)); memcpy((uint8_t*)ctx->pin_a.p + n * sizeof(ImageDesc), offs.data(), n * 8);
+        CK(cudaMemcpyAsync(ctx->imgs.p, ctx->pin_a.p, n * sizeof(ImageDesc), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->offs.p, (uint8_t*)ctx->pin_a.p + n * sizeof(ImageDesc), n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(k_store7, dim3(296, n), 256, 0, (const ImageDesc*)ctx->imgs.p, (const uint64_t*)ctx->offs.p, dout);
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        if (!out_on_device) {
+            if (used > out_cap) { CK(cudaStreamSynchronize(ctx->stream)); FAIL("output buffer too small: need %llu bytes, have %llu", (unsigned long long)used, (unsigned long long)out_cap); }
+            CK(cudaMemcpyAsync(out, dout, used, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+        return 0;
+    }
+    // ---- chunks on lanes
+    const std::vector<uint32_t> cuts = cut_chunks(ctx, imgs, n);
+    const uint32_t nchunks = (uint32_t)cuts.size() - 1;
+    uint64_t tiles_est = 0;
+    for (uint32_t i = 0; i < n; i++) tiles_est += (imgs[i].w * imgs[i].h + TILE_AREA - 1) / TILE_AREA;
+    // kernel family by the size of the CALL (what is in flight at once), not of a chunk
+    const bool lat = (level == 2 ? 17 * tiles_est <= (uint64_t)ctx->lat_max_blocks * 5 / 2 : 9 * tiles_est <= ctx->lat_max_blocks);
+    std::vector<EncChunk> chunks(nchunks);
+    uint64_t host_packed = 0;   // host output: files are packed across chunks
+    int rc = 0;
+    auto harvest = [&](uint32_t ci) -> int {   // finish chunk ci; host output: start its D2H copy on its lane
+        EncChunk& C = chunks[ci];
+        xpngb_ctx* lane = C.lane;
+        if (encode_finish(lane, C)) return 1;
+        if (!out_on_device) {
+            const uint64_t len = C.used_end - C.out_base;
+            if (host_packed + len > out_cap) FAIL("output buffer too small: need more than %llu bytes, have %llu", (unsigned long long)(host_packed + len), (unsigned long long)out_cap);
+            CK(cudaMemcpyAsync((uint8_t*)out + host_packed, dout + C.out_base, len, cudaMemcpyDeviceToHost, lane->stream));
+            for (uint32_t i = 0; i < C.n; i++) C.out_offsets[i] = C.out_offsets[i] - C.out_base + host_packed;
+            host_packed += len;
+        }
+        return 0;
+    };
+    uint64_t region = 0;
+    uint32_t harvested = 0;
+    for (uint32_t ci = 0; ci < nchunks && !rc; ci++) {
+        const uint32_t li = ci % ctx->pipe_lanes;
+        while (!rc && ci >= ctx->pipe_lanes && harvested <= ci - ctx->pipe_lanes) rc = harvest(harvested++);   // the lane's previous chunk must be done
+        if (rc) break;
+        xpngb_ctx* lane = lane_get(ctx, li);
+        if (!lane) { snprintf(ctx->err, sizeof ctx->err, "cannot create pipeline lane %u", li); rc = 1; break; }
+        EncChunk& C = chunks[ci];
+        C.lane = lane; C.imgs = imgs + cuts[ci]; C.n = cuts[ci + 1] - cuts[ci];
+        C.out_offsets = out_offsets + cuts[ci]; C.out_sizes = out_sizes + cuts[ci];
+        C.out_base = region; region += xpngb_encode_bound(C.imgs, C.n); C.out_end = region;
+        if (lane != ctx) { if (cudaStreamWaitEvent(lane->stream, ctx->ev0, 0) != cudaSuccess) { snprintf(ctx->err, sizeof ctx->err, "cudaStreamWaitEvent failed"); rc = 1; break; } }
+        if (!pixels_on_device) {   // the chunk's pixel range (images of a chunk are adjacent in every sane layout; any layout is correct)
+            uint64_t lo = ~0ull, hi = 0;
+            for (uint32_t i = 0; i < C.n; i++) {
+                const uint64_t a = C.imgs[i].offset, b = a + C.imgs[i].w * C.imgs[i].h * (3 + (C.imgs[i].A ? 1 : 0));
+                if (a < lo) lo = a; if (b > hi) hi = b;
             }
-            ENSURE(imgs, n * sizeof(ImageDesc)); ENSURE(offs, n * 8);
-            if (ensure_pin(ctx, ctx->pin_a, n * (sizeof(ImageDesc) + 8))) return 1;
-            memcpy(ctx->pin_a.p, I.data(), n * sizeof(ImageDesc)); memcpy((uint8_t*)ctx->pin_a.p + n * sizeof(ImageDesc), offs.data(), n * 8);
-            CK(cudaMemcpyAsync(ctx->imgs.p, ctx->pin_a.p, n * sizeof(ImageDesc), cudaMemcpyHostToDevice, ctx->stream));
-            CK(cudaMemcpyAsync(ctx->offs.p, (uint8_t*)ctx->pin_a.p + n * sizeof(ImageDesc), n * 8, cudaMemcpyHostToDevice, ctx->stream));
-            LAUNCH(k_store7, dim3(296, n), 256, 0, (const ImageDesc*)ctx->imgs.p, (const uint64_t*)ctx->offs.p, dout);
-        } else if (encode_chunk(ctx, 7, imgs, n, dpix, dout, 0, out_on_device ? out_cap : bound, out_offsets, out_sizes, &used)) return 1;
-    } else {
-        uint32_t i0 = 0;
-        while (i0 < n) {
-            uint64_t px = 0; uint32_t i1 = i0;
-            while (i1 < n && (i1 == i0 || px + imgs[i1].w * imgs[i1].h <= ctx->max_chunk_px)) { px += imgs[i1].w * imgs[i1].h; i1++; }
-            if (encode_chunk(ctx, level, imgs + i0, i1 - i0, dpix, dout, used, out_on_device ? out_cap : bound, out_offsets + i0,
-                             out_sizes + i0, &used)) return 1;
-            i0 = i1;
+            if (cudaMemcpyAsync((uint8_t*)ctx->pixels.p + lo, (const uint8_t*)pixels + lo, hi - lo, cudaMemcpyHostToDevice, lane->stream) != cudaSuccess) {
+                snprintf(ctx->err, sizeof ctx->err, "host to device copy failed"); rc = 1; break;
+            }
         }
+        rc = encode_issue(lane, level, lat, dpix, dout, C);
     }
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    if (!out_on_device) {
-        if (used > out_cap) {   // sizes are known only now; fail cleanly like a short write would
-            CK(cudaStreamSynchronize(ctx->stream));
-            FAIL("output buffer too small: need %llu bytes, have %llu", (unsigned long long)used, (unsigned long long)out_cap);
-        }
-        CK(cudaMemcpyAsync(out, dout, used, cudaMemcpyDeviceToHost, ctx->stream));
+    while (!rc && harvested < nchunks) rc = harvest(harvested++);
+    // join: the root stream waits for every lane, so that ev1 closes the whole call
+    for (uint32_t li = 1; li < ctx->pipe_lanes && li <= ctx->lanes.size(); li++) {
+        xpngb_ctx* lane = ctx->lanes[li - 1];
+        cudaEventRecord(lane->ev_done, lane->stream);
+        cudaStreamWaitEvent(ctx->stream, lane->ev_done, 0);
     }
-    CK(cudaStreamSynchronize(ctx->stream));
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !rc) { snprintf(ctx->err, sizeof ctx->err, "device error: %s", cudaGetErrorString(cudaGetLastError())); rc = 1; }
+    if (rc) { for (xpngb_ctx* l : ctx->lanes) cudaStreamSynchronize(l->stream); return 1; }
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     return 0;
 }
@@ -598,7 +760,8 @@ static int orient_check(xpngb_ctx* ctx, int op, const xpngb_image* imgs, uint32_
         const xpngb_image& m = imgs[i];
         if (!m.w || !m.h || m.w > (1u << 24) || m.h > (1u << 24)) FAIL("image %u: bad dimensions", i);
         if (m.offset & 15) FAIL("image %u: pixel offset must be a multiple of 16", i);
-        if (m.offset + m.w * m.h * (3 + (m.A ? 1 : 0)) > size) FAIL("image %u: pixels exceed the buffer", i);
+        const uint64_t bytes = m.w * m.h * (3 + (m.A ? 1 : 0));
+        if (bytes > size || m.offset > size - bytes) FAIL("image %u: pixels exceed the buffer", i);
     }
     return 0;
 }
@@ -609,6 +772,10 @@ extern "C" int xpngb_transform(xpngb_ctx* ctx, int op, xpngb_image* imgs, uint32
     ctx->err[0] = 0; ctx->launches = 0; ctx->last_ms = 0.f; ctx->cur = ctx->stream;
     if (!imgs || !src || !dst) FAIL("null argument");
     if (src == dst) FAIL("in-place orientation is not supported");
+    if (!src_on_device == !dst_on_device) {   // same side: the two byte ranges must be disjoint
+        const uintptr_t a = (uintptr_t)src, b = (uintptr_t)dst;
+        if (a < b + size && b < a + size) FAIL("source and destination pixel buffers overlap");
+    }
     if (orient_check(ctx, op, imgs, n, size)) return 1;
     if (n == 0) return 0;
     CK(cudaSetDevice(ctx->device));
@@ -649,60 +816,47 @@ extern "C" int xpngb_encode_oriented(xpngb_ctx* ctx, int level, int op, xpngb_im
     const uint32_t l0 = ctx->launches;
     const int rc = xpngb_encode(ctx, level, imgs, n, ctx->oriented.p, pixels_size, 1, out, out_cap, out_on_device, out_offsets, out_sizes);
     ctx->launches += l0;
+    if (rc && (op == OP_R90 || op == OP_R270))   // failed: hand the descriptors back in the caller's orientation
+        for (uint32_t i = 0; i < n; i++) { const uint64_t t = imgs[i].w; imgs[i].w = imgs[i].h; imgs[i].h = t; }
     return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Decode
 // ------------------------------------------------------------------------------------------------
-extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const void* files, uint64_t files_size, int files_on_device,
-                            const uint64_t* file_offsets, const uint64_t* file_sizes, void* pixels, uint64_t pixels_cap,
-                            int pixels_on_device) {
-    if (!ctx) return 1;
-    ctx->err[0] = 0; ctx->launches = 0; ctx->last_ms = 0.f; ctx->cur = ctx->stream;
-    if (!imgs || !files || !file_offsets || !file_sizes || !pixels) FAIL("null argument");
-    if (n == 0) return 0;
-    CK(cudaSetDevice(ctx->device));
-    for (uint32_t i = 0; i < n; i++) {
-        if (file_sizes[i] < 11 || file_offsets[i] + file_sizes[i] > files_size) FAIL("file %u: bad offset/size", i);
-    }
-    const uint8_t* din = (const uint8_t*)files;
-    if (!files_on_device) {
-        ENSURE(files, files_size);
-        CK(cudaMemcpyAsync(ctx->files.p, files, files_size, cudaMemcpyHostToDevice, ctx->stream));
-        din = (const uint8_t*)ctx->files.p;
-    }
-    // ---- headers (libxpng.c:969-973)
-    std::vector<uint32_t> hdr(2 * n);
-    if (!files_on_device) {
-        for (uint32_t i = 0; i < n; i++) memcpy(&hdr[2 * i], (const uint8_t*)files + file_offsets[i], 8);
-    } else {
-        ENSURE(offs, n * 8); ENSURE(hdr, n * 8);
-        if (ensure_pin(ctx, ctx->pin_a, n * 8)) return 1;
-        memcpy(ctx->pin_a.p, file_offsets, n * 8);
-        CK(cudaMemcpyAsync(ctx->offs.p, ctx->pin_a.p, n * 8, cudaMemcpyHostToDevice, ctx->stream));
-        LAUNCH(k_gather_headers, (n + 127) / 128, 128, 0, din, (const uint64_t*)ctx->offs.p, n, (uint32_t*)ctx->hdr.p);
-        CK(cudaMemcpyAsync(hdr.data(), ctx->hdr.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-    }
-    uint8_t* dpx = (uint8_t*)pixels;
-    if (!pixels_on_device) { ENSURE(pixels, pixels_cap); dpx = (uint8_t*)ctx->pixels.p; }
+// Work lists of the pair decoders (dec_rans_pair.cuh): two sets, one per level family present in the chunk.
+static size_t pdw_bytes(uint32_t cap) { return (size_t)(2 * PD_NCLASS * PD_BUCKETS + PD_NCLASS + 5) * 4 + (size_t)PD_NCLASS * cap * 4; }
+static PdWork pdw_at(void* base, uint32_t cap) {
+    uint32_t* p = (uint32_t*)base;
+    PdWork W; W.hist = p; W.start = p + PD_NCLASS * PD_BUCKETS; W.total = p + 2 * PD_NCLASS * PD_BUCKETS; W.order = W.total + PD_NCLASS + 5; W.cap = cap;
+    return W;
+}
+
+// Launch the decode of one chunk on lane `ctx`.  hdr: the two header words of each file.  `lat`: warp-per-block chain
+// kernels (few blocks in the whole call) instead of the pair decoders.  Never waits for the device.
+static int decode_issue(xpngb_ctx* ctx, bool lat, xpngb_image* imgs, uint32_t n, const uint32_t* hdr, const uint8_t* din,
+                        const uint64_t* file_offsets, const uint64_t* file_sizes, uint8_t* dpx, uint64_t pixels_cap, uint32_t call_tiles) {
+    ctx->cur = ctx->stream;
     Plan P;
     std::vector<DecImage> DI(n);
     bool any1 = false, any2 = false;
     for (uint32_t i = 0; i < n; i++) {
         const uint64_t w = (hdr[2 * i] & 0xFFFFFFu) + 1, h = (hdr[2 * i + 1] & 0xFFFFFFu) + 1;
         const uint32_t A = (hdr[2 * i + 1] >> 24) & 1, mode = hdr[2 * i] >> 24, pxsz = 3 + A;
-        if (!(mode == 1 || mode == 2 || mode == 7)) FAIL("file %u: unknown mode %u", i, mode);   // libxpng.c:972
-        if (imgs[i].w && (imgs[i].w != w || imgs[i].h != h)) FAIL("file %u: header %llux%llu does not match the descriptor", i,
+        if (!(mode == 1 || mode == 2 || mode == 7)) FAIL("file: unknown mode %u", mode);   // libxpng.c:972
+        if (imgs[i].w && (imgs[i].w != w || imgs[i].h != h)) FAIL("file: header %llux%llu does not match the descriptor",
                                                                    (unsigned long long)w, (unsigned long long)h);
         imgs[i].w = w; imgs[i].h = h; imgs[i].A = A; imgs[i].mode = mode;
         const uint64_t s = w * h * pxsz;
-        if (imgs[i].offset & 15) FAIL("file %u: pixel offset must be a multiple of 16", i);
-        if (imgs[i].offset + s > pixels_cap) FAIL("file %u: pixels exceed the output buffer", i);
+        if (imgs[i].offset & 15) FAIL("file: pixel offset must be a multiple of 16");
+        if (s > pixels_cap || imgs[i].offset > pixels_cap - s) FAIL("file: pixels exceed the output buffer");
         uint32_t m = mode;
-        if (mode == 7) { if (file_sizes[i] < 8 + s) FAIL("file %u: truncated stored image", i); }
+        if (mode == 7) { if (file_sizes[i] < 8 + s) FAIL("file: truncated stored image"); }
         else if (file_sizes[i] == 11 + A && ((hdr[2 * i + 1] >> 24) & 2)) m = mode | 0x100;      // libxpng.c:976
+        // dimensions come from an untrusted header and size every scratch buffer below: a tile is at most 666 x 666 pixels and
+        // its blob at least 8 bytes, so a coded file shorter than that cannot hold the image it claims
+        else if (file_sizes[i] < 8 + 8 * (w * h / (666ull * 666ull))) FAIL("file: %llu bytes cannot hold a %llux%llu image",
+                                                                           (unsigned long long)file_sizes[i], (unsigned long long)w, (unsigned long long)h);
         any1 |= m == 1; any2 |= m == 2;
         DecImage& D = DI[i];
         D.file_off = file_offsets[i]; D.file_size = file_sizes[i]; D.px_off = imgs[i].offset; D.w = (uint32_t)w; D.h = (uint32_t)h;
@@ -712,6 +866,7 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
         plan_image(P, (uint64_t)(dpx + imgs[i].offset), DI[i].w, DI[i].h, DI[i].pxsz, DI[i].mode, any2 ? 4 : 1, 0);
         DI[i].tile0 = P.imgs[i].tile0; DI[i].ntiles = P.imgs[i].ntiles;
     }
+    if (P.tiles.size() > (1u << 24) || P.seg_tile.size() > (1u << 28)) FAIL("too many tiles for one chunk (%zu)", P.tiles.size());
     const uint32_t ntiles = (uint32_t)P.tiles.size();
     if (upload_plan(ctx, P)) return 1;
     ENSURE(dimgs, n * sizeof(DecImage)); ENSURE(dtiles, ntiles * sizeof(DecTile)); ENSURE(errflag, 4);
@@ -732,70 +887,105 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
     const DecImage* d_imgs = (const DecImage*)ctx->dimgs.p;
     DecTile* d_dt = (DecTile*)ctx->dtiles.p;
     int* d_err = (int*)ctx->errflag.p;
-    CK(cudaEventRecord(ctx->ev0, ctx->stream));
     const uint32_t nseg = (uint32_t)P.seg_tile.size();
     const uint32_t* d_seg_tile = (const uint32_t*)ctx->seg_tile.p;
     bool side_busy[xpngb_ctx::NSIDE] = {};
+    const uint32_t pd_cap = 17u * ntiles;
     if (any1 || any2) {
         ENSURE(streams, P.str_total); ENSURE(nlseq, P.px_total); ENSURE(rows, P.row_total * sizeof(RowInfo));
         ENSURE(rowcnt, P.row_total * 4); ENSURE(edge, P.row_total * 16);
         ENSURE(ccnt, (size_t)nseg * 9 * 4); ENSURE(cbit, (size_t)nseg * 4); ENSURE(resv, P.px_total * 4);
         if (P.any_rgba) { ENSURE(alpha, P.px_total); ENSURE(plane, P.px_total); }
+        if (!lat) { ENSURE(pdw, 2 * pdw_bytes(pd_cap)); CK(cudaMemsetAsync(ctx->pdw.p, 0, 2 * pdw_bytes(pd_cap), ctx->stream)); }
         LAUNCH(k_dec_tile_offsets, (n + 127) / 128, 128, 0, d_imgs, din, d_dt, n, d_err);
     }
-    // Stream plan of one decode call.  Main stream: the level-2 family (or the only family).  side[2]: the level-1 family
-    // when both are present in the batch (config 0: the corpus mixes RGB and RGBA files).  side[0], side[1]: level-2
+    // Stream plan of one chunk.  Main stream: the level-2 family (or the only family).  side[2]: the level-1 family
+    // when both are present (config 0: the corpus mixes RGB and RGBA files).  side[0], side[1]: level-2
     // value streams.  side[3]: the alpha plane.  Each family's chain is parse -> context rANS -> context walk.
     uint32_t maxpx = 0;
     for (const TileDesc& t : P.tiles) if (t.npx > maxpx) maxpx = t.npx;
     const uint32_t wsm = (maxpx / 8 + 32) * 4;          // nibble-packed streams of the largest tile + pad words
+    PdWork Wl[3] = {};                              // work lists of the pair decoders / the batch walk, per level family
     auto launch_walk = [&](uint32_t mode) -> int {
         WalkArgs wa{ d_tiles, d_imgs, d_dt, (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->nlseq.p, ntiles, mode };
-        // the shared-memory walk only pays when every tile's CTA is resident at once (no waves): 227 KB per SM, 148 SMs
+        if (!lat && !ctx->root->walk_ring && !ctx->root->walk_global) {   // batches: three tiles per warp, longest tiles first
+            const PdWork& W = Wl[mode];
+            LAUNCH(k_dec_walk3<2>, (ntiles + 5) / 6, 64, 0, wa, (const uint32_t*)(W.order + (size_t)PD_WALK * W.cap), (const uint32_t*)(W.total + PD_WALK));
+            return 0;
+        }
+        // the shared-memory walk only pays when every tile's CTA of the CALL is resident at once (no waves): 227 KB per SM, 148 SMs
         const uint32_t resident = 148u * ((227u * 1024u) / (wsm + 1024u));
-        if (ntiles <= resident && maxpx <= WALK_SMEM_MAX_SYMS && !ctx->walk_ring && !ctx->walk_global) LAUNCH(k_dec_walk_smem<0>, ntiles, 32, wsm, wa);
-        else if (ctx->walk_global) {                   // XPNGB_WALK=global: the older variant with refills straight from global memory
+        xpngb_ctx* r = ctx->root;
+        if (call_tiles <= resident && maxpx <= WALK_SMEM_MAX_SYMS && !r->walk_ring && !r->walk_global) LAUNCH(k_dec_walk_smem<0>, ntiles, 32, wsm, wa);
+        else if (r->walk_global) {                     // XPNGB_WALK=global: the older variant with refills straight from global memory
             if (ntiles <= 592) LAUNCH(k_dec_walk_lat<1>, ntiles, 32, 0, wa);
             else LAUNCH(k_dec_walk_lat<4>, (ntiles + 3) / 4, 128, 0, wa);
         }
-        else if (ntiles <= 592) LAUNCH(k_dec_walk_ring<1>, ntiles, 32, 0, wa);
+        else if (call_tiles <= 592) LAUNCH(k_dec_walk_ring<1>, ntiles, 32, 0, wa);
         else LAUNCH(k_dec_walk_ring<4>, (ntiles + 3) / 4, 128, 0, wa);
         return 0;
     };
+    // pair decoders of one level family: work lists, run / raw fills, then one launch per class
+    auto pd_lists = [&](uint32_t mode, PdWork& W) -> int {
+        W = pdw_at((uint8_t*)ctx->pdw.p + (mode == 1 ? 0 : pdw_bytes(pd_cap)), pd_cap);
+        const unsigned g = (17u * ntiles + 255) / 256;
+        LAUNCH(k_pd_count, g, 256, 0, d_tiles, d_imgs, (const DecTile*)d_dt, ntiles, mode, W);
+        LAUNCH(k_pd_scan, PD_NCLASS, 1024, 0, W);
+        LAUNCH(k_pd_fill, g, 256, 0, d_tiles, d_imgs, (const DecTile*)d_dt, ntiles, mode, W);
+        return 0;
+    };
+    auto pd_args = [&](const PdWork& W, int cls) {
+        return PairDecArgs{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, (uint8_t*)ctx->alpha.p, W.order + (size_t)cls * W.cap, W.total + cls, d_err };
+    };
+    auto pd_grid = [&](uint32_t per_tile) { return (unsigned)(((uint64_t)per_tile * ntiles + PD_BLK * PD_WARPS - 1) / (PD_BLK * PD_WARPS)); };
     if (any1) {
         const bool own_stream = any2;                   // level-1 family next to a level-2 family
         cudaStream_t f1 = own_stream ? ctx->side[2] : ctx->stream;
         if (own_stream) { FORK_SIDE(2); side_busy[2] = true; }
         LAUNCH(k_dec_parse_m1, (ntiles + 127) / 128, 128, 0, d_tiles, d_imgs, din, d_dt, ntiles, d_err);
-        RansDecArgs ra{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, (uint8_t*)ctx->alpha.p, ntiles, 0, 9 };
-        const bool lat = 9 * ntiles <= ctx->lat_max_blocks;
-        if (P.any_rgba) {                             // the alpha plane is independent of the context walk
-            FORK_FROM(f1, 3); side_busy[3] = true;
-            RansDecArgs rb = ra; rb.c0 = 9; rb.nc = 1;
-            auto k_dec_rans_v2_lat_alpha = k_dec_rans_v2_lat;
-            if (lat) LAUNCH(k_dec_rans_v2_lat_alpha, ntiles, 32, lat_smem(LUT_TWO_15), rb, LUT_TWO_15);
-            else LAUNCH(k_dec_rans_v2_big<32>, (ntiles + 31) / 32, 32, 32 * 258 * 2 + 32 * 260, rb);
-            AlphaArgs al{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->alpha.p, (uint8_t*)ctx->plane.p, (uint32_t*)ctx->rowcnt.p };
-            LAUNCH(k_dec_alpha, ntiles, 256, 0, al);
-            LAUNCH(k_dec_rows_rgba, ntiles, 32, 0, d_tiles, d_imgs, (const DecTile*)d_dt, (const uint32_t*)ctx->rowcnt.p, (RowInfo*)ctx->rows.p);
+        RansDecArgs ra{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, (uint8_t*)ctx->alpha.p, ntiles, 0, 9, d_err };
+        AlphaArgs al{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->alpha.p, (uint8_t*)ctx->plane.p, (uint32_t*)ctx->rowcnt.p };
+        if (lat) {
+            if (P.any_rgba) {                             // the alpha plane is independent of the context walk
+                FORK_FROM(f1, 3); side_busy[3] = true;
+                RansDecArgs rb = ra; rb.c0 = 9; rb.nc = 1;
+                auto k_dec_rans_v2_lat_alpha = k_dec_rans_v2_lat;
+                LAUNCH(k_dec_rans_v2_lat_alpha, ntiles, 32, lat_smem(LUT_TWO_15), rb, LUT_TWO_15);
+                LAUNCH(k_dec_alpha, ntiles, 256, 0, al);
+                LAUNCH(k_dec_rows_rgba, ntiles, 32, 0, d_tiles, d_imgs, (const DecTile*)d_dt, (const uint32_t*)ctx->rowcnt.p, (RowInfo*)ctx->rows.p);
+            }
+            ctx->cur = f1;
+            const uint32_t lut12 = call_tiles <= ctx->root->v2_direct_max_tiles ? LUT_ONE_12 : LUT_TWO_12;
+            LAUNCH(k_dec_rans_v2_lat, 9 * ntiles, 32, lat_smem(lut12), ra, lut12);
+        } else {
+            PdWork& W = Wl[1];
+            if (pd_lists(1, W)) return 1;
+            PdFillArgs fa{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, (uint8_t*)ctx->alpha.p, ntiles, 1 };
+            LAUNCH(k_pd_fill_blocks, (17u * ntiles + 3) / 4, 128, 0, fa);
+            if (P.any_rgba) {
+                FORK_FROM(f1, 3); side_busy[3] = true;
+                auto k_dec_rans_pair_v2_alpha = k_dec_rans_pair<2, 0>;
+                LAUNCH(k_dec_rans_pair_v2_alpha, pd_grid(1), PD_WARPS * 32, PD_WARPS * PD_BIG_BYTES, pd_args(W, PD_BIG));
+                LAUNCH(k_dec_alpha, ntiles, 256, 0, al);
+                LAUNCH(k_dec_rows_rgba, ntiles, 32, 0, d_tiles, d_imgs, (const DecTile*)d_dt, (const uint32_t*)ctx->rowcnt.p, (RowInfo*)ctx->rows.p);
+            }
+            ctx->cur = f1;
+            auto k_dec_rans_pair_v2_ctx = k_dec_rans_pair<2, 8>;
+            LAUNCH(k_dec_rans_pair_v2_ctx, pd_grid(9), PD_WARPS * 32, 0, pd_args(W, PD_S8));
         }
-        ctx->cur = f1;
-        const uint32_t lut12 = ntiles <= ctx->v2_direct_max_tiles ? LUT_ONE_12 : LUT_TWO_12;
-        if (lat) LAUNCH(k_dec_rans_v2_lat, 9 * ntiles, 32, lat_smem(lut12), ra, lut12);
-        else LAUNCH(k_dec_rans_v2_small<128>, (9 * ntiles + 127) / 128, 128, 0, ra);
         if (launch_walk(1)) return 1;
         BACK_TO_MAIN();
     }
     if (any2) {
         LAUNCH(k_dec_parse_m2, (ntiles + 127) / 128, 128, 0, d_tiles, d_imgs, din, d_dt, ntiles, d_err);
-        if (17 * ntiles <= ctx->lat_max_blocks * 5 / 2) {
+        if (lat) {
             // value streams on the side streams (joined before the residual kernels); LAT_M2_ORDER: 0..2 alphabets of at
             // most 16 symbols (direct table, 64 KiB), 3..7 larger alphabets (two-level), 8..16 contexts, 17 grey plane
             // a batch with more chains than fit next to 64 KiB tables (3 per SM) trades the shorter dependent step of the
             // direct table for residency: two-level tables (17 KiB) keep 12 chains per SM
-            const bool direct = ntiles <= ctx->direct_max_tiles;
+            const bool direct = call_tiles <= ctx->root->direct_max_tiles;
             const uint32_t lut16 = direct ? LUT_ONE_14 : LUT_TWO_14;
-            RansV1LatArgs la{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 3, lut16, 0u, ~0u };
+            RansV1LatArgs la{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 3, lut16, 0u, ~0u, d_err };
             auto k_dec_rans_v1_lat_values16 = k_dec_rans_v1_lat; auto k_dec_rans_v1_lat_values256 = k_dec_rans_v1_lat;
             auto k_dec_rans_v1_lat_grey = k_dec_rans_v1_lat; auto k_dec_rans_v1_lat_ctx = k_dec_rans_v1_lat;   // names for the profile report
             auto k_dec_rans_v1_lat_ctx_short = k_dec_rans_v1_lat;
@@ -820,15 +1010,19 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
                 JOIN_SIDE(4); side_busy[4] = false;       // the walk needs every context stream
             } else LAUNCH(k_dec_rans_v1_lat_ctx, 9 * ntiles, 32, lat_smem(LUT_TWO_14), la);
         } else {
-        RansV1DecArgs rv{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 9, 0, 16 };
-        auto k_dec_rans_v1_lane_8 = k_dec_rans_v1_small<8, 128>; auto k_dec_rans_v1_lane_15 = k_dec_rans_v1_small<15, 128>; auto k_dec_rans_v1_lane_big = k_dec_rans_v1_big<32>;
-        LAUNCH(k_dec_rans_v1_lane_8, (9 * ntiles + 127) / 128, 128, 0, rv);                     // contexts (9 symbols); grey tiles: nothing (N = 256)
-        rv.c0 = 9; rv.nc = 8;
-        LAUNCH(k_dec_rans_v1_lane_15, (8 * ntiles + 127) / 128, 128, 0, rv);                    // value alphabets of 8 / 16 symbols
-        rv.nmin = 16; rv.nmax = 256;
-        LAUNCH(k_dec_rans_v1_lane_big, (8 * ntiles + 31) / 32, 32, 32 * 258 * 2 + 32 * 260, rv); // value alphabets of 32..256 symbols
-        rv.c0 = 0; rv.nc = 1;
-        LAUNCH(k_dec_rans_v1_lane_big, (ntiles + 31) / 32, 32, 32 * 258 * 2 + 32 * 260, rv);     // grey planes
+            // the value streams (16-symbol alphabet: the longest chains of a tile; large alphabets) start first on the side
+            // streams; contexts and the 8-symbol value streams on the main stream, followed by the walk
+            PdWork& W = Wl[2];
+            if (pd_lists(2, W)) return 1;
+            PdFillArgs fa{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, (uint8_t*)ctx->alpha.p, ntiles, 2 };
+            auto k_dec_rans_pair_v1_s16 = k_dec_rans_pair<1, 15>; auto k_dec_rans_pair_v1_big = k_dec_rans_pair<1, 0>; auto k_dec_rans_pair_v1_s8 = k_dec_rans_pair<1, 8>;
+            FORK_SIDE(0); side_busy[0] = true;
+            LAUNCH(k_dec_rans_pair_v1_s16, pd_grid(1), PD_WARPS * 32, 0, pd_args(W, PD_S16));
+            FORK_SIDE(1); side_busy[1] = true;
+            LAUNCH(k_dec_rans_pair_v1_big, pd_grid(5), PD_WARPS * 32, PD_WARPS * PD_BIG_BYTES, pd_args(W, PD_BIG));
+            LAUNCH(k_pd_fill_blocks, (17u * ntiles + 3) / 4, 128, 0, fa);
+            BACK_TO_MAIN();
+            LAUNCH(k_dec_rans_pair_v1_s8, pd_grid(11), PD_WARPS * 32, 0, pd_args(W, PD_S8));
         }
         if (launch_walk(2)) return 1;
     }
@@ -845,26 +1039,122 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
                        (uint4*)ctx->edge.p, 0 };
         uint32_t maxw = 0;
         for (const TileDesc& t : P.tiles) if (t.w > maxw) maxw = t.w;
-        // 16 warps per tile when tiles are fewer than SMs (shortest band pipeline), 8 otherwise (two CTAs per SM)
-        if (ntiles <= 148) LAUNCH(k_dec_unpredict_rows<16>, ntiles, 16 * 32, 16 * 2 * 32 * UNR_PITCH, ua);
-        else LAUNCH(k_dec_unpredict_rows<8>, ntiles, 8 * 32, 8 * 2 * 32 * UNR_PITCH, ua);
+        // 16 warps per tile when the call has fewer tiles than SMs (shortest band pipeline), 8 up to a few per SM; beyond
+        // that one warp per tile: bands of a tile depend on each other, so extra warps only wait on the band above, and
+        // with thousands of tiles the tiles themselves are the parallelism
+        uint32_t nw = call_tiles <= 148 ? 16u : (call_tiles <= ctx->root->unr_multi_max_tiles ? 8u : 1u);
+        if (ctx->root->unr_force) nw = ctx->root->unr_force;
+        if (nw == 16) LAUNCH(k_dec_unpredict_rows<16>, ntiles, 16 * 32, 16 * 2 * 32 * UNR_PITCH, ua);
+        else if (nw == 8) LAUNCH(k_dec_unpredict_rows<8>, ntiles, 8 * 32, 8 * 2 * 32 * UNR_PITCH, ua);
+        else if (nw == 4) LAUNCH(k_dec_unpredict_rows<4>, ntiles, 4 * 32, 4 * 2 * 32 * UNR_PITCH, ua);
+        else if (nw == 2) LAUNCH(k_dec_unpredict_rows<2>, ntiles, 2 * 32, 2 * 2 * 32 * UNR_PITCH, ua);
+        else LAUNCH(k_dec_unpredict_rows<1>, ntiles, 32, 2 * 32 * UNR_PITCH, ua);
         ua.min_w = UNR_MAXW;
         if (maxw > UNR_MAXW) LAUNCH(k_dec_unpredict, ntiles, UNP_THREADS, 0, ua);   // very wide, flat tiles only
         if (any2) LAUNCH(k_dec_grey_raw, ntiles, 256, 0, d_tiles, d_imgs, (const DecTile*)d_dt, din);
     }
     if (any7) LAUNCH(k_load7, dim3(296, n), 256, 0, (const ImageDesc*)ctx->imgs.p, (const uint64_t*)ctx->offs.p, din);   // stored images: flat copies
     LAUNCH(k_dec_copy, ntiles, 256, 0, d_tiles, d_imgs, (const DecTile*)d_dt, din, (uint8_t*)nullptr);
-    CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    int herr = 0;
-    CK(cudaMemcpyAsync(&herr, d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (!pixels_on_device) {
-        uint64_t hi = 0;
-        for (uint32_t i = 0; i < n; i++) { const uint64_t e = imgs[i].offset + imgs[i].w * imgs[i].h * (3 + imgs[i].A); if (e > hi) hi = e; }
-        CK(cudaMemcpyAsync(pixels, dpx, hi, cudaMemcpyDeviceToHost, ctx->stream));
+    // the error flag travels to pinned memory behind the DecImage table
+    CK(cudaMemcpyAsync((uint8_t*)ctx->pin_b.p + n * (sizeof(DecImage) + 8), d_err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+}
+
+extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const void* files, uint64_t files_size, int files_on_device,
+                            const uint64_t* file_offsets, const uint64_t* file_sizes, void* pixels, uint64_t pixels_cap,
+                            int pixels_on_device) {
+    if (!ctx) return 1;
+    ctx->err[0] = 0; ctx->launches = 0; ctx->last_ms = 0.f; ctx->cur = ctx->stream;
+    if (!imgs || !files || !file_offsets || !file_sizes || !pixels) FAIL("null argument");
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    for (uint32_t i = 0; i < n; i++) {
+        if (file_sizes[i] < 11 || file_sizes[i] > files_size || file_offsets[i] > files_size - file_sizes[i]) FAIL("file %u: bad offset/size", i);
     }
-    CK(cudaStreamSynchronize(ctx->stream));
+    const uint8_t* din = (const uint8_t*)files;
+    if (!files_on_device) { ENSURE(files, files_size); din = (const uint8_t*)ctx->files.p; }
+    // ---- headers (libxpng.c:969-973)
+    std::vector<uint32_t> hdr(2 * n);
+    if (!files_on_device) {
+        for (uint32_t i = 0; i < n; i++) memcpy(&hdr[2 * i], (const uint8_t*)files + file_offsets[i], 8);
+    } else {
+        ENSURE(offs, n * 8); ENSURE(hdr, n * 8);
+        if (ensure_pin(ctx, ctx->pin_a, n * 8)) return 1;
+        memcpy(ctx->pin_a.p, file_offsets, n * 8);
+        CK(cudaMemcpyAsync(ctx->offs.p, ctx->pin_a.p, n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        LAUNCH(k_gather_headers, (n + 127) / 128, 128, 0, din, (const uint64_t*)ctx->offs.p, n, (uint32_t*)ctx->hdr.p);
+        CK(cudaMemcpyAsync(hdr.data(), ctx->hdr.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    uint8_t* dpx = (uint8_t*)pixels;
+    if (!pixels_on_device) { ENSURE(pixels, pixels_cap); dpx = (uint8_t*)ctx->pixels.p; }
+    // chunks are cut by the header dimensions (validated per chunk in decode_issue)
+    std::vector<xpngb_image> dims(n);
+    uint64_t tiles_est = 0; bool l2 = false;
+    for (uint32_t i = 0; i < n; i++) {
+        dims[i].w = (hdr[2 * i] & 0xFFFFFFu) + 1; dims[i].h = (hdr[2 * i + 1] & 0xFFFFFFu) + 1;
+        const uint32_t mode = hdr[2 * i] >> 24;
+        if (mode == 1 || mode == 2) tiles_est += (dims[i].w * dims[i].h + TILE_AREA - 1) / TILE_AREA;
+        l2 |= mode == 2;
+    }
+    const bool lat = l2 ? 17 * tiles_est <= (uint64_t)ctx->lat_max_blocks * 5 / 2 : 9 * tiles_est <= ctx->lat_max_blocks;
+    const std::vector<uint32_t> cuts = cut_chunks(ctx, dims.data(), n);
+    const uint32_t nchunks = (uint32_t)cuts.size() - 1;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    int rc = 0;
+    std::vector<xpngb_ctx*> used(nchunks, nullptr);
+    std::vector<uint32_t> cn(nchunks, 0);
+    auto chunk_done = [&](uint32_t ci) -> int {   // wait for chunk ci, read its error flag
+        xpngb_ctx* lane = used[ci];
+        CK(cudaStreamSynchronize(lane->stream));
+        int herr = 0; memcpy(&herr, (uint8_t*)lane->pin_b.p + cn[ci] * (sizeof(DecImage) + 8), 4);
+        if (herr) FAIL("corrupt .xpng data (decoder error %d)", herr);
+        return 0;
+    };
+    uint32_t done = 0;
+    for (uint32_t ci = 0; ci < nchunks && !rc; ci++) {
+        const uint32_t li = ci % ctx->pipe_lanes;
+        while (!rc && ci >= ctx->pipe_lanes && done <= ci - ctx->pipe_lanes) rc = chunk_done(done++);
+        if (rc) break;
+        xpngb_ctx* lane = lane_get(ctx, li);
+        if (!lane) { snprintf(ctx->err, sizeof ctx->err, "cannot create pipeline lane %u", li); rc = 1; break; }
+        used[ci] = lane; cn[ci] = cuts[ci + 1] - cuts[ci];
+        const uint32_t i0 = cuts[ci], m = cn[ci];
+        if (lane != ctx && cudaStreamWaitEvent(lane->stream, ctx->ev0, 0) != cudaSuccess) { snprintf(ctx->err, sizeof ctx->err, "cudaStreamWaitEvent failed"); rc = 1; break; }
+        if (!files_on_device) {
+            uint64_t lo = ~0ull, hi = 0;
+            for (uint32_t i = i0; i < i0 + m; i++) { if (file_offsets[i] < lo) lo = file_offsets[i]; if (file_offsets[i] + file_sizes[i] > hi) hi = file_offsets[i] + file_sizes[i]; }
+            if (cudaMemcpyAsync((uint8_t*)ctx->files.p + lo, (const uint8_t*)files + lo, hi - lo, cudaMemcpyHostToDevice, lane->stream) != cudaSuccess) {
+                snprintf(ctx->err, sizeof ctx->err, "host to device copy failed"); rc = 1; break;
+            }
+        }
+        rc = decode_issue(lane, lat, imgs + i0, m, hdr.data() + 2 * i0, din, file_offsets + i0, file_sizes + i0, dpx, pixels_cap, (uint32_t)(tiles_est > 0xFFFFFFFFull ? 0xFFFFFFFFu : tiles_est));
+        if (!rc && !pixels_on_device) {
+            uint64_t lo = ~0ull, hi = 0;
+            for (uint32_t i = i0; i < i0 + m; i++) {
+                const uint64_t a = imgs[i].offset, b = a + imgs[i].w * imgs[i].h * (3 + imgs[i].A);
+                if (a < lo) lo = a; if (b > hi) hi = b;
+            }
+            if (cudaMemcpyAsync((uint8_t*)pixels + lo, dpx + lo, hi - lo, cudaMemcpyDeviceToHost, lane->stream) != cudaSuccess) {
+                snprintf(ctx->err, sizeof ctx->err, "device to host copy failed"); rc = 1;
+            }
+        }
+    }
+    // every issued chunk is waited for, also after an error (the caller's buffers must be quiet when we return)
+    for (; done < nchunks; done++) {
+        if (!used[done]) continue;
+        if (rc) cudaStreamSynchronize(used[done]->stream);
+        else rc = chunk_done(done);
+    }
+    for (uint32_t li = 1; li <= ctx->lanes.size(); li++) {
+        xpngb_ctx* lane = ctx->lanes[li - 1];
+        cudaEventRecord(lane->ev_done, lane->stream);
+        cudaStreamWaitEvent(ctx->stream, lane->ev_done, 0);
+    }
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    if (rc) return 1;
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
-    if (herr) FAIL("corrupt .xpng data (decoder error %d)", herr);
     return 0;
 }
 

@@ -37,7 +37,7 @@ __global__ void k_dec_parse_m2(const TileDesc* tiles, const DecImage* imgs, cons
         uint32_t bsz = bad ? 4 : ld32u(blob + 4);
         if (bsz < 4 || (uint64_t)4 + bsz > d->size) bad = true;
         const uint8_t* kend = blob + 4 + bsz;
-        uint32_t off = 4 + bsz, bit = grey ? 8 : 24, soff = 0, nsym = 0;
+        uint32_t off = 4 + bsz, bit = grey ? 8 : 24, soff = 0, nsym = 0, nval = 0;
         for (int c = 0; c < nblk && !bad; c++) {
             if (off + 4 > d->size) { bad = true; break; }
             const uint32_t N = grey ? 256u : (uint32_t)DEC_M2_NSYM[c], nbit = bitlen32(N - 1);
@@ -57,11 +57,15 @@ __global__ void k_dec_parse_m2(const TileDesc* tiles, const DecImage* imgs, cons
             }
             soff += align16u_dec(n);
             if (c < 9) nsym += n;
+            // the value blocks together hold at most three bytes per coded pixel: anything above that would run past the
+            // tile's slice of the stream scratch ((align16(npx) + 256) * 4 bytes), so it is refused before any rANS kernel runs
+            else { nval += n; if (nval > 3 * (t.npx - 1)) { bad = true; break; } }
             off += bsize;
         }
         if (!bad && nsym != t.npx - 1 && !grey) bad = true;
         if (!bad && grey && d->blk[0].n != t.npx - 1) bad = true;
         if (!bad && (uint64_t)bit > 8ull * (bsz - 4)) bad = true;
+        if (!bad && (uint64_t)soff > ((uint64_t)align16u_dec(t.npx) + 256) * 4) bad = true;
         d->bsz = bsz; d->nsym = grey ? t.npx - 1 : nsym;
     } else bad = true;
     if (bad) { dec_fail(err, DEC_BAD_BLOCK); d->m = 0xFE; }
@@ -516,13 +520,17 @@ constexpr int UNR_PITCH = 32 * 4 + 4;   // bytes per staged row chunk (32 pixels
 // two 32-column chunks of its band in shared memory and writes a finished chunk row by row (contiguous bytes).
 template <int PXSZ>
 __device__ __forceinline__ void unr_flush(const uint8_t* sb, uint8_t* dst, const TileDesc& t, uint32_t y0, uint32_t chunk, uint32_t lane) {
-    const uint32_t ncols = min(32u, t.w - 32u * chunk), nbytes = ncols * PXSZ;
+    const uint32_t ncols = min(32u, t.w - 32u * chunk), nbytes = ncols * PXSZ, nw = nbytes >> 2;
     const uint8_t* src = sb + (chunk & 1u) * (32 * UNR_PITCH);
+    const uint32_t nrows = min(32u, t.h - y0);
+    uint8_t* o = dst + (uint64_t)y0 * t.bpr + (uint64_t)PXSZ * 32u * chunk;
 #pragma unroll 4
-    for (uint32_t r = 0; r < 32; r++) {
-        if (y0 + r >= t.h) break;
-        uint8_t* o = dst + (uint64_t)(y0 + r) * t.bpr + (uint64_t)PXSZ * 32u * chunk;
-        for (uint32_t k = lane; k < nbytes; k += 32) o[k] = src[r * UNR_PITCH + k];
+    for (uint32_t r = 0; r < nrows; r++, o += t.bpr, src += UNR_PITCH) {
+        if ((reinterpret_cast<uintptr_t>(o) & 3u) == 0) {          // warp-uniform; a staged row starts word-aligned (UNR_PITCH = 132)
+            if (lane < nw) reinterpret_cast<uint32_t*>(o)[lane] = reinterpret_cast<const uint32_t*>(src)[lane];
+            const uint32_t k = (nw << 2) + lane;                    // a narrow last chunk may end inside a word
+            if (k < nbytes) o[k] = src[k];
+        } else for (uint32_t k = lane; k < nbytes; k += 32) o[k] = src[k];
     }
 }
 
@@ -597,46 +605,57 @@ __device__ __forceinline__ void unpredict_rows(const UnpredArgs& A, const TileDe
                 }
             } else { anext = prow[0]; rnext = res[idx]; }
         }
-        const uint32_t steps = w + 31;
+        const uint32_t steps = (w + 31 + RING - 1) / RING * RING;   // whole rings: the extra steps find every lane past its row
         uint32_t flushed = 0;                                // chunks written out so far
+        const bool row0 = y == 0;
+        const uint32_t stage_lane = lane * UNR_PITCH;
         for (uint32_t s0 = 0; s0 < steps; s0 += RING) {
 #pragma unroll
             for (int j = 0; j < RING; j++) {
                 const uint32_t s = s0 + j;
-                if (s >= steps) break;
-                if (b && (s & 7u) == 0) {                    // lane 0 will need columns s .. s + 7 of the band above
+                if (NW > 1 && b && j == 0) {                 // lane 0 will need columns s .. s + 7 of the band above
                     const uint32_t need = upbase + min(s + 8u, w);
                     while (prog[upidx] < need) { }
                     __syncwarp();
                 }
-                const uint32_t x = s - lane;
-                const bool act = rowok && s >= lane && x < w;
+                const uint32_t x = s - lane;                 // lanes that have not started yet wrap around: x >= w
+                const bool act = rowok && x < w;
+                // U: the pixel the lane above produced in the previous step; lane 0 takes it from the boundary row of the band
+                // above (band 0 has none, and never uses it: its lane 0 is image row 0, predicted from the left)
+                const uint32_t ub = upbrow[min(s, w - 1)];
                 uint32_t U = __shfl_up_sync(0xffffffffu, prevout, 1);
-                if (lane == 0) U = (b && x < w) ? upbrow[x] : 0u;
+                U = lane == 0 ? ub : U;
                 uint32_t pix = 0;
                 const uint32_t rv3 = rn[j];                  // static ring index: slot j <-> steps s == j (mod RING)
+                if (PXSZ == 3) {
+                    // refill slot j for the step RING steps from now.  A predicated load straight INTO the ring register: written
+                    // as `rn[j] = __ldg(..)` inside the branch below, the compiler loads into a temporary and moves it at once,
+                    // which waits for the whole memory latency on every step (ncu: 40 % of the kernel's stall samples sat on that move).
+                    // The index is clamped into the row (row 0 has no residual at x = 0: rrow[0] would be the word before the slice).
+                    const uint32_t xi = max(min(x + RING, w - 1), row0 ? 1u : 0u);
+                    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q ld.global.nc.u32 %0, [%1];\n}"
+                                 : "+r"(rn[j]) : "l"(rrow + xi), "r"((uint32_t)act));
+                }
                 if (act) {
-                    bool coded = !(x == 0 && y == 0);
+                    const bool origin = (x | y) == 0;
+                    bool coded = !origin;
                     const uint32_t a = anext, rv = PXSZ == 3 ? rv3 : rnext;
                     if (PXSZ == 4) {
                         if (a == 0) coded = false;
                         if (coded) idx++;
                         if (x + 1 < w) anext = prow[x + 1];
                         rnext = res[idx];                    // the slice has slack behind its last residual
-                    } else {
-                        // consumed RING steps from now; the index is clamped into the row (row 0 has no residual at x = 0:
-                        // rrow[0] would be the word before the tile's slice), so the loaded value never needs a select
-                        rn[j] = __ldg(rrow + max(min(x + RING, w - 1), y ? 0u : 1u));
                     }
-                    // all three channels at once
-                    uint32_t r = swar_unzz(rv & 0x00FFFFFFu);
-                    if (GSUB && x && y) r = swar_add(r, ((r >> 8) & 0xFFu) * 0x00010001u);
-                    const uint32_t l3 = left & 0x00FFFFFFu, u3 = U & 0x00FFFFFFu, q3 = uprev & 0x00FFFFFFu;
+                    // all three channels at once (byte 3 of every operand is zero for RGB; RGBA keeps alpha there and masks it)
+                    uint32_t r = swar_unzz(PXSZ == 3 ? rv : (rv & 0x00FFFFFFu));
+                    if (GSUB) { const uint32_t rg = swar_add(r, ((r >> 8) & 0xFFu) * 0x00010001u); r = (x && !row0) ? rg : r; }
+                    const uint32_t l3 = PXSZ == 3 ? left : (left & 0x00FFFFFFu), u3 = PXSZ == 3 ? U : (U & 0x00FFFFFFu),
+                                   q3 = PXSZ == 3 ? uprev : (uprev & 0x00FFFFFFu);
                     uint32_t pd = PM == 0 ? l3 : (PM == 1 ? u3 : (PM == 2 ? swar_avg2(l3, u3) : swar_grad3(l3, u3, q3)));
-                    pd = y == 0 ? l3 : (x == 0 ? u3 : pd);
+                    pd = row0 ? l3 : (x == 0 ? u3 : pd);
                     const uint32_t val = (swar_add(r, pd) & 0x00FFFFFFu) | (PXSZ == 4 ? (a << 24) : 0u);
-                    pix = (x == 0 && y == 0) ? first : (coded ? val : 0u);
-                    uint8_t* o = sb + ((x >> 5) & 1u) * (32 * UNR_PITCH) + lane * UNR_PITCH + PXSZ * (x & 31u);
+                    pix = origin ? first : (coded ? val : 0u);
+                    uint8_t* o = sb + stage_lane + (x & 32u) * UNR_PITCH + PXSZ * (x & 31u);
                     if (PXSZ == 4) *reinterpret_cast<uint32_t*>(o) = pix;
                     else { o[0] = (uint8_t)pix; o[1] = (uint8_t)(pix >> 8); o[2] = (uint8_t)(pix >> 16); }
                     left = pix;
@@ -644,11 +663,11 @@ __device__ __forceinline__ void unpredict_rows(const UnpredArgs& A, const TileDe
                 }
                 uprev = U;
                 prevout = pix;
-                if (lane == lastlane && act && ((x & 7u) == 7u || x == w - 1)) {   // publish progress of the band's last row
+                if (NW > 1 && lane == lastlane && act && ((x & 7u) == 7u || x == w - 1)) {   // publish progress of the band's last row
                     __threadfence_block();
                     prog[wid] = seq * stride + x + 1;
                 }
-                if (s >= 62 && ((s - 62) & 31u) == 0) {      // every lane has finished chunk (s - 62) / 32
+                if (j == RING - 2 && (s & 31u) == 30u && s >= 62) {   // every lane has finished chunk (s - 62) / 32
                     __syncwarp();
                     unr_flush<PXSZ>(sb, dst, t, b * 32, flushed, lane);
                     flushed++;

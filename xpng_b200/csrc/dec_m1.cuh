@@ -120,6 +120,7 @@ struct RansDecArgs {
     uint8_t* alpha;       // alpha symbols at px_off
     uint32_t ntiles;
     uint32_t c0, nc;
+    int* err;
 };
 
 // decode step shared by all variants: x' = f*(x>>pb) + slot - start, then renormalise from *rp backwards

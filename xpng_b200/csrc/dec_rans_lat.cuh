@@ -221,12 +221,19 @@ __global__ void __launch_bounds__(32) k_dec_rans_v2_lat(RansDecArgs A, uint32_t 
     const uint32_t N = v2 + 2, w2 = ld32u(blk + 8); const int pb = (int)(w2 >> 24);
     const uint32_t tabw = w2 & 0xFFFFFFu;
     const bool two = N > 16 || (4u << pb) > lut_bytes;
-    if (N > 256 || pb < 10 || pb > 15 || 8 + 4ull * tabw > csz || tabw < 5 || (two && (1u << pb) + 1024u > lut_bytes)) {
+    // a context stream never has more than 9 symbols: a larger alphabet is corrupt data and is refused here exactly as in
+    // the lane-per-block kernel (k_dec_rans_v2_small), so both families agree on corrupt input
+    if (N > 256 || (ctx && N > 16) || pb < 10 || pb > 15 || 8 + 4ull * tabw > csz || tabw < 5 || (two && (1u << pb) + 1024u > lut_bytes)) {
         for (uint32_t k = lane; k < n; k += 32) out[k] = 0;
         return;
     }
     const uint8_t* tab = blk + 8 + 4ull * tabw;
     lat_read_table(cum, tab, blk + csz, 0, N, pb, b.type == 4, lane);
+    if (cum[N] != (1u << pb)) {   // a valid table sums to 2^PROB_BITS exactly (libxpng.c:316-329); refused in both kernel families
+        if (lane == 0) dec_fail(A.err, DEC_BAD_BLOCK);
+        for (uint32_t k = lane; k < n; k += 32) out[k] = 0;
+        return;
+    }
     uint32_t* tab2 = lut; uint8_t* sym8 = reinterpret_cast<uint8_t*>(lut + 256);
     if (two) lat_build_lut2(sym8, tab2, cum, N, pb, lane); else lat_build_lut1(lut, cum, N, pb, lane, ctx);
     __syncwarp();
@@ -254,6 +261,7 @@ struct RansV1LatArgs {
     uint32_t j0, nj;        // range of LAT_M2_ORDER handled by this launch
     uint32_t lut_bytes;
     uint32_t n_lo, n_hi;    // only blocks with n_lo <= symbols < n_hi (long and short blocks get differently sized tables)
+    int* err;
 };
 
 __global__ void __launch_bounds__(32) k_dec_rans_v1_lat(RansV1LatArgs A) {
@@ -285,6 +293,11 @@ __global__ void __launch_bounds__(32) k_dec_rans_v1_lat(RansV1LatArgs A) {
     const bool two = N > 16 || (4u << pb) > A.lut_bytes;
     if (two && (1u << pb) + 1024u > A.lut_bytes) { for (uint32_t k = lane; k < n; k += 32) out[k] = 0; return; }
     lat_read_table(cum, side, side_end, bitpos, N, pb, b.type == 4, lane);
+    if (cum[N] != (1u << pb)) {   // see k_dec_rans_v2_lat
+        if (lane == 0) dec_fail(A.err, DEC_BAD_BLOCK);
+        for (uint32_t k = lane; k < n; k += 32) out[k] = 0;
+        return;
+    }
     uint32_t* tab2 = lut; uint8_t* sym8 = reinterpret_cast<uint8_t*>(lut + 256);
     if (two) lat_build_lut2(sym8, tab2, cum, N, pb, lane); else lat_build_lut1(lut, cum, N, pb, lane, ctx);
     __syncwarp();

@@ -164,6 +164,7 @@ struct FrontArgs {
     uint8_t* alpha_area;          // per tile at px_off: raster-order alpha symbols (index raster-1)
     uint32_t* hist;               // per tile: HIST_STRIDE u32
     uint16_t* vcnt;               // mode 2: [nseg_total][9] value-chunk element counts
+    uint32_t rgba_only;           // 1: RGB tiles are handled by k_front2 (enc_front2.cuh), this launch only takes the RGBA ones
 };
 
 constexpr int HIST_CTX = 0;        // [9][16] context histograms
@@ -359,6 +360,7 @@ __global__ void __launch_bounds__(FRONT_THREADS, XPB_FRONT_MINB) k_front(FrontAr
     const uint32_t gseg = blockIdx.x, tile = A.seg_tile[gseg];
     const TileDesc t = A.tiles[tile];
     if (MODE == 2 && A.tile_skip && A.tile_skip[tile]) return;
+    if (A.rgba_only && t.pxsz != 4) return;
     if (MODE == 1 && t.pxsz == 4) front_segment<MODE, 4>(A, S, t, tile, gseg);
     else front_segment<MODE, 3>(A, S, t, tile, gseg);
 }
