@@ -1,21 +1,28 @@
 #!/usr/bin/env python
-"""bench.py — xPNG encode/decode MPix/s at -1/-2/-7 on B200 (BASELINE.json metric), one JSON line.
+"""bench.py — xPNG encode/decode MPix/s on B200 (BASELINE.json metric), one JSON line.
 
-A "step" is one pass of the hot path over one batch: encode the workload's frame(s) at levels
-1, 2 and 7 and decode each result (6 codec calls).  Workload at every N: configs[1] of BASELINE.json,
-one 3840x2160 RGB synthetic frame per GPU (seed 1 + rank, SURVEY.md §8(d) generator); with N ranks
-each rank codes its own frame (frames are independent: weak scaling, no data-path collective).
+Workload: BASELINE configs[2] — a fixed batch of F sintel-like 1920x1080 RGB frames (seeds 1000.., SURVEY.md §8(d);
+F = 1000 unless --frames / XPNG_BENCH_FRAMES says otherwise), cut contiguously over the N ranks with
+xpngb_shard_range (STRONG scaling: the batch is fixed, every rank codes its shard on its own GPU with no data-path
+collective).  A "step" is one pass of the hot path over the batch:
 
-  value : whole-job MPix/s (pixels through the 6 calls, all ranks) with inputs and outputs resident
-          in HBM, timed with CUDA events on the codec's stream, max over ranks.
-  e2e   : the same step through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region).
+    for level in (1, 2):  encode shard  ->  size/offset gather over all ranks (C, shared memory)  ->  decode shard
+
+  value : whole-job MPix/s = 4 codec calls x batch pixels / step time, pixels and files resident in HBM, CUDA events
+          on the codec's stream, max over ranks.  Level 7 (a device copy) is measured on its own and reported in
+          `breakdown`, not folded into `value`.
+  e2e   : the same step through the C ABI with pinned HOST buffers (H2D and D2H inside the timed region).
+  breakdown : per level and direction ms, MPix/s and algorithmic GB/s; level 7; a single 3840x2160 frame (configs[1])
+          as the `latency` record; `e2e_file`: the repo's own xpng_store_T / xpng_load_T through tmpfs.
   roofline / cpu_baseline: see DESIGN.md "Measurement".
 
---impl reference times the unmodified reference (oracle/_ref, built from /root/reference by
-oracle/Makefile) on the host cores with all the threads it spawns by itself (T = 0 -> nproc).
+--impl reference times the unmodified reference (oracle/_ref, built from /root/reference by oracle/Makefile) on the
+host cores with all the threads it spawns by itself (T = 0 -> nproc), on a bounded sample of the same frames, through
+its own file API on tmpfs.
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -27,12 +34,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-W, H = 3840, 2160
-LEVELS = (1, 2, 7)
-# the levels of a step are independent jobs: level 2 (the longest chains) gets a host thread of its own, levels 1 and 7
-# share the second one (tools/e2e_probe.py: a third pipeline in flight only adds PCIe contention to level 2's copies)
-PIPELINES = ((2,), (1, 7))
-METRIC = "xpng encode+decode MPix/s over levels -1/-2/-7"
+FW, FH = 1920, 1080
+SEED0 = 1000
+LEVELS = (1, 2)
+METRIC = "xpng encode+decode MPix/s at levels -1/-2 over a 1080p frame batch"
+REF_SAMPLE = 64
 
 
 def peaks():
@@ -58,8 +64,7 @@ class ClockSampler(threading.Thread):
             N.nvmlInit()
             h = N.nvmlDeviceGetHandleByIndex(self.index)
             mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
-            bits = {"hw_slowdown": N.nvmlClocksEventReasonHwSlowdown if hasattr(N, "nvmlClocksEventReasonHwSlowdown") else 0x8,
-                    "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
             get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
         except Exception:
             return False
@@ -101,7 +106,7 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------ reference arm
 
 def _quiet_call(fn, *a):
-    """Run fn with fd 1 pointed at /dev/null (the reference prints a MPx/s line per call)."""
+    """Run fn with fd 1 pointed at /dev/null (the reference prints a MPx/s line per call, NCCL its version)."""
     sys.stdout.flush()
     saved = os.dup(1)
     devnull = os.open(os.devnull, os.O_WRONLY)
@@ -118,69 +123,113 @@ class _Xpng(C.Structure):
     _fields_ = [("p", C.c_void_p), ("w", C.c_uint64), ("h", C.c_uint64), ("s", C.c_uint64), ("A", C.c_bool)]
 
 
-def reference_steps(frame, steps, warmup):
-    """Time the CPU baseline: K steps (encode + decode at levels 1/2/7) of the reference's own code.
-    Returns (seconds per step list, kind, cores, sample)."""
-    from oracle import pyoracle as po
-    tmp = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
-    ref_so = os.path.join(ROOT, "oracle", "_ref", "libxpng_ref.so")
-    times = []
-    if os.path.exists(ref_so):
-        L = C.CDLL(ref_so)
-        L.xpng_store_T.restype = C.c_bool
-        L.xpng_store_T.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(_Xpng), C.c_char_p]
-        L.xpng_load_T.restype = C.c_bool
-        L.xpng_load_T.argtypes = [C.c_uint64, C.c_char_p, C.POINTER(_Xpng)]
-        libc = C.CDLL(None)
-        libc.free.argtypes = [C.c_void_p]
-        pm = _Xpng(frame.ctypes.data, frame.shape[1], frame.shape[0], frame.size, frame.shape[2] == 4)
-        paths = {lv: os.path.join(tmp, f"_xpng_ref_{os.getpid()}_{lv}.xpng").encode() for lv in LEVELS}
+def _tmpdir():
+    return "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
 
-        def step():
-            for lv in LEVELS:
-                assert not L.xpng_store_T(0, lv, C.byref(pm), paths[lv])
-            for lv in LEVELS:
+
+def file_api_steps(L, frames, steps, warmup, tag):
+    """K steps of the file-at-a-time API (xpng_store_T / xpng_load_T, T = 0) over `frames` at levels 1 and 2, files on tmpfs.
+    `L` is a CDLL exporting the reference's entry points (the reference itself or this repo's drop-in).
+    Returns (seconds per step, {call: seconds per step})."""
+    L.xpng_store_T.restype = C.c_bool
+    L.xpng_store_T.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(_Xpng), C.c_char_p]
+    L.xpng_load_T.restype = C.c_bool
+    L.xpng_load_T.argtypes = [C.c_uint64, C.c_char_p, C.POINTER(_Xpng)]
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    pms = [_Xpng(f.ctypes.data, f.shape[1], f.shape[0], f.size, f.shape[2] == 4) for f in frames]
+    paths = [os.path.join(_tmpdir(), f"_xpng_{tag}_{os.getpid()}_{i}.xpng").encode() for i in range(len(frames))]
+    per_call = {}
+
+    def step(rec):
+        for lv in LEVELS:
+            t0 = time.perf_counter()
+            for pm, p in zip(pms, paths):
+                assert not L.xpng_store_T(0, lv, C.byref(pm), p)
+            t1 = time.perf_counter()
+            for p in paths:
                 out = _Xpng()
-                assert not L.xpng_load_T(0, paths[lv], C.byref(out))
+                assert not L.xpng_load_T(0, p, C.byref(out))
                 libc.free(C.c_void_p(out.p))
+            t2 = time.perf_counter()
+            if rec:
+                per_call[f"enc{lv}"] = per_call.get(f"enc{lv}", 0.0) + (t1 - t0)
+                per_call[f"dec{lv}"] = per_call.get(f"dec{lv}", 0.0) + (t2 - t1)
+    times = []
+    try:
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            _quiet_call(step)
+            _quiet_call(step, i >= warmup)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
-        for p in paths.values():
+    finally:
+        for p in paths:
             if os.path.exists(p):
                 os.remove(p)
-        return times, "reference", os.cpu_count(), "same 3840x2160 frame, levels 1/2/7 encode+decode via xpng_store_T/xpng_load_T (T=0: all host cores), files on tmpfs"
-    # the unmodified reference did not travel: time the single-threaded oracle port instead
-    def step():
-        for lv in LEVELS:
-            f = po.encode(lv, frame)
-            po.decode(f)
+    return sum(times) / len(times), {k: v / steps for k, v in per_call.items()}
+
+
+def reference_steps(frames, steps, warmup):
+    """CPU baseline on `frames`: the unmodified reference when it travelled (oracle/_ref), else the oracle port."""
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libxpng_ref.so")
+    if os.path.exists(ref_so):
+        per_step, calls = file_api_steps(C.CDLL(ref_so), frames, steps, warmup, "ref")
+        return per_step, calls, "reference", os.cpu_count(), "xpng_store_T/xpng_load_T (T=0: all host cores), files on tmpfs"
+    from oracle import pyoracle as po
+    calls = {}
+    t_all = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        step()
+        for lv in LEVELS:
+            ta = time.perf_counter()
+            files = [po.encode(lv, f) for f in frames]
+            tb = time.perf_counter()
+            for f in files:
+                po.decode(f)
+            tc = time.perf_counter()
+            if i >= warmup:
+                calls[f"enc{lv}"] = calls.get(f"enc{lv}", 0.0) + (tb - ta) / steps
+                calls[f"dec{lv}"] = calls.get(f"dec{lv}", 0.0) + (tc - tb) / steps
         if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    return times, "port", 1, "same 3840x2160 frame, levels 1/2/7 encode+decode with the single-threaded oracle port"
+            t_all.append(time.perf_counter() - t0)
+    return sum(t_all) / len(t_all), calls, "port", 1, "single-threaded oracle port, in memory"
+
+
+def call_table(calls, npx_total):
+    return {k: {"ms": round(v * 1e3, 3), "MPix_s": round(npx_total / 1e6 / v, 1)} for k, v in sorted(calls.items())}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     from xpng_b200 import synth
-    frame = synth.rgb(H, W, 1)
-    steps = max(1, min(args.steps, 20))
-    times, kind, cores, sample = reference_steps(frame, steps, min(args.warmup, 2))
-    per_step = sum(times) / len(times)
-    value = 6 * W * H / 1e6 / per_step
-    line = {"metric": METRIC, "value": round(value, 2), "unit": "MPix/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 2),
-            "ms_per_step": round(per_step * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+    nf = min(args.frames, REF_SAMPLE)
+    frames = synth.sintel_batch(range(SEED0, SEED0 + nf))
+    steps = max(1, min(args.steps, 10))
+    per_step, calls, kind, cores, how = reference_steps(frames, steps, args.warmup)
+    npx = nf * FW * FH
+    value = 4 * npx / 1e6 / per_step
+    sample = f"first {nf} of the {args.frames} frames, levels 1 and 2, encode then decode of every frame per level, {how}"
+    line = {"metric": METRIC, "value": round(value, 2), "unit": "MPix/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": round(per_step * 1e3, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": "configs[1]: one 3840x2160 RGB synthetic frame, levels -1/-2/-7, encode+decode", "host_threads": cores},
+            "config": workload_config(args.frames, world, sample_frames=nf),
             "cpu_baseline": {"value": round(value, 2), "unit": "MPix/s", "cores": cores, "kind": kind, "sample": sample},
-            "e2e": {"value": round(value, 2), "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": round(value, 2), "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "breakdown": call_table(calls, npx)}
     print(json.dumps(line), flush=True)
+
+
+def workload_config(frames, world, sample_frames=None):
+    cfg = {"workload": f"configs[2]: {frames} sintel-like 1920x1080 RGB frames (seeds {SEED0}..{SEED0 + frames - 1}), levels -1/-2, "
+                       "encode + size/offset gather + decode per level",
+           "frames": frames, "tiles_per_frame": 8,
+           "l2": "no flush needed: a rank's pixels, files and scratch are far larger than the 126 MB L2 (>= 0.7 GB per rank at N = 8)",
+           "parallelism": f"frames sharded contiguously over {world} GPU(s) (xpngb_shard_range), no data-path collective; "
+                          "one shared-memory size gather per level (xpngb_gather_sizes, C, no NCCL)"}
+    if sample_frames is not None:
+        cfg["reference_sample_frames"] = sample_frames
+    return cfg
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -188,211 +237,274 @@ def run_reference(args, rank, world):
 def run_ours(args, rank, world, local_rank):
     import torch
     import xpng_b200
-    from xpng_b200 import synth
+    from xpng_b200 import shard, synth
     from oracle import pyoracle as po
 
     dist = None
     if world > 1:
-        import torch.distributed as dist
+        import torch.distributed as dist                      # the clock only: barrier + max over ranks
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
-        # the communicator is created here (eagerly, or by the barrier): NCCL announces its version on stdout, which must
-        # carry ONE JSON line, so fd 1 points at /dev/null meanwhile
         _quiet_call(lambda: (dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank)), dist.barrier()))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    # one codec context (= its own CUDA streams and scratch) per level: the three levels of a step are
-    # independent jobs, so they are issued concurrently from host threads, see PIPELINES (ctypes drops the GIL)
-    cds = {lv: xpng_b200.Codec(local_rank) for lv in LEVELS}
-    cd = cds[1]
-    stream = torch.cuda.ExternalStream(cd.stream, device=dev)
     lib = xpng_b200.lib()
-    from concurrent.futures import ThreadPoolExecutor
-    pool = ThreadPoolExecutor(max_workers=len(PIPELINES))
-
-    frame = synth.rgb(H, W, 1 + rank)
-    npx = W * H
-    descs, total = xpng_b200.Codec.layout([frame.shape])
-    cap = int(lib.xpngb_encode_bound(descs, 1))
-    # device-resident buffers
-    d_px = torch.from_numpy(frame.reshape(-1)).to(dev)
-    d_px = torch.cat([d_px, torch.zeros(64, dtype=torch.uint8, device=dev)])
+    cd = xpng_b200.Codec(local_rank)
+    stream = torch.cuda.ExternalStream(cd.stream, device=dev)
+    F = args.frames
+    lo, hi = shard.shard_range(F, rank, world)
+    n = hi - lo
+    gather = shard.Gather(f"bench{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', os.getppid() if world > 1 else os.getpid())}",
+                          rank, world, F)
+    npx_frame = FW * FH
+    shapes = [(FH, FW, 3)] * n
+    descs0, total = xpng_b200.Codec.layout(shapes)
+    cap = int(lib.xpngb_encode_bound(descs0, n)) if n else 16
+    # ---- frames of this rank's shard, generated straight into pinned host memory, then uploaded
+    h_px = torch.empty(max(total, 16) + 64, dtype=torch.uint8).pin_memory()
+    frames_sample = {}
+    if n:
+        hv = h_px.numpy()
+        sample_idx = sorted({0, n // 3, (2 * n) // 3, n - 1})
+        for k0 in range(0, n, 64):
+            part = synth.sintel_batch(range(SEED0 + lo + k0, SEED0 + lo + min(k0 + 64, n)))
+            for k, f in enumerate(part):
+                o = descs0[k0 + k].offset
+                hv[o:o + f.size] = f.reshape(-1)
+                if k0 + k in sample_idx:
+                    frames_sample[k0 + k] = f
+    d_px = h_px.to(dev)
     d_files = {lv: torch.zeros(cap + 64, dtype=torch.uint8, device=dev) for lv in LEVELS}
-    d_back = {lv: torch.zeros(total + 64, dtype=torch.uint8, device=dev) for lv in LEVELS}
-    # pinned host buffers for the e2e leg
-    h_px = torch.from_numpy(frame.reshape(-1).copy()).pin_memory()
-    h_files = {lv: torch.zeros(cap + 64, dtype=torch.uint8).pin_memory() for lv in LEVELS}
-    h_back = {lv: torch.zeros(total + 64, dtype=torch.uint8).pin_memory() for lv in LEVELS}
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    sizes = {}
-    launches = [0]
+    d_back = torch.zeros(max(total, 16) + 64, dtype=torch.uint8, device=dev)
+    state = {"launches": 0, "calls": {}, "sizes": {}, "offs": {}, "table_sha": None}
 
-    def enc_one(lv, px, files, on_dev):
-        d = xpng_b200.Codec.layout([frame.shape])[0]
-        offs, sz = cds[lv].encode_raw(lv, d, 1, px.data_ptr(), total, on_dev, files[lv].data_ptr(), cap, on_dev)
-        sizes[lv] = (int(offs[0]), int(sz[0]))
-        return cds[lv].last_launches
+    def new_descs(zero_dims=False):
+        d = xpng_b200.Codec.layout(shapes)[0]
+        if zero_dims:
+            for x in d:
+                x.w = x.h = 0
+        return d
 
-    def dec_one(lv, files, back, on_dev):
-        d = xpng_b200.Codec.layout([frame.shape])[0]
-        d[0].w = d[0].h = 0
-        off = (C.c_uint64 * 1)(sizes[lv][0]); sz = (C.c_uint64 * 1)(sizes[lv][1])
-        cds[lv].decode_raw(d, 1, files[lv].data_ptr(), cap, on_dev, off, sz, back[lv].data_ptr(), total, on_dev)
-        return cds[lv].last_launches
-
-    def step(px, files, back, on_dev):
-        # per level: encode, then decode of that level's file; the pipelines of PIPELINES are in flight together
-        launches[0] += sum(pool.map(lambda lvs: sum(enc_one(lv, px, files, on_dev) + dec_one(lv, files, back, on_dev) for lv in lvs), PIPELINES))
+    def step(px, files, back, on_dev, rec):
+        h = hashlib.sha256()
+        for lv in LEVELS:
+            t0 = time.perf_counter()
+            if n:
+                offs, sz = cd.encode_raw(lv, new_descs(), n, px.data_ptr(), total, on_dev, files[lv].data_ptr(), files[lv].numel() - 64, on_dev)
+                state["launches"] += cd.last_launches
+            else:
+                offs, sz = (C.c_uint64 * 1)(), (C.c_uint64 * 1)()
+            t1 = time.perf_counter()
+            g_offs, g_sizes = gather.sizes(F, [int(sz[i]) for i in range(n)])       # the one exchange between ranks
+            h.update(np.asarray(g_sizes, dtype=np.uint64).tobytes()); h.update(np.asarray(g_offs, dtype=np.uint64).tobytes())
+            t2 = time.perf_counter()
+            if n:
+                cd.decode_raw(new_descs(True), n, files[lv].data_ptr(), files[lv].numel() - 64, on_dev, offs, sz, back.data_ptr(), total, on_dev)
+                state["launches"] += cd.last_launches
+            t3 = time.perf_counter()
+            state["sizes"][lv] = [int(sz[i]) for i in range(n)]; state["offs"][lv] = [int(offs[i]) for i in range(n)]
+            if rec:
+                c = state["calls"]
+                c[f"enc{lv}"] = c.get(f"enc{lv}", 0.0) + (t1 - t0); c[f"gather{lv}"] = c.get(f"gather{lv}", 0.0) + (t2 - t1)
+                c[f"dec{lv}"] = c.get(f"dec{lv}", 0.0) + (t3 - t2)
+        state["table_sha"] = h.hexdigest()[:16]
 
     def timed(px, files, back, on_dev, steps, warmup):
         for _ in range(warmup):
-            step(px, files, back, on_dev)
+            step(px, files, back, on_dev, False)
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
-        launches[0] = 0
-        ms = 0.0
+        state["launches"] = 0; state["calls"] = {}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
         for _ in range(steps):
-            flush.fill_(1)                      # L2 flush between timed iterations (outside the events)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            step(px, files, back, on_dev)
-            e1.record(stream)
-            e1.synchronize()
-            ms += e0.elapsed_time(e1)
+            step(px, files, back, on_dev, True)
+        e1.record(stream)
+        e1.synchronize()
         torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.barrier()
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return float(t.item()), {k: v / steps for k, v in state["calls"].items()}
 
-    # parity gate before any timing counts: bytes and pixels against the oracle
-    step(d_px, d_files, d_back, 1)
+    # ---- parity gate before any timing counts: sampled frames byte for byte against the oracle,
+    # every decoded pixel of the shard against the input
+    step(d_px, d_files, d_back, 1, False)
     for lv in LEVELS:
-        o, s = sizes[lv]
-        got = d_files[lv][o:o + s].cpu().numpy().tobytes()
-        assert got == po.encode(lv, frame), f"level {lv}: bytes differ from the oracle"
-    for lv in LEVELS:
-        assert np.array_equal(d_back[lv][:frame.size].cpu().numpy(), frame.reshape(-1)), f"level {lv}: decoded pixels differ"
-    xpng_bytes = {lv: sizes[lv][1] for lv in LEVELS}
+        for k, f in frames_sample.items():
+            o, s = state["offs"][lv][k], state["sizes"][lv][k]
+            got = d_files[lv][o:o + s].cpu().numpy().tobytes()
+            assert got == po.encode(lv, f), f"rank {rank} level {lv} frame {lo + k}: bytes differ from the oracle"
+    for lv in LEVELS:   # decoded pixels (the last level's decode is in d_back; redo level 1 to check both)
+        if n:
+            cd.decode_raw(new_descs(True), n, d_files[lv].data_ptr(), cap, 1, (C.c_uint64 * n)(*state["offs"][lv]), (C.c_uint64 * n)(*state["sizes"][lv]),
+                          d_back.data_ptr(), total, 1)
+            assert torch.equal(d_back[:total], d_px[:total]), f"rank {rank} level {lv}: decoded pixels differ"
+    xpng_bytes = {lv: sum(state["sizes"][lv]) for lv in LEVELS}
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_dev = timed(d_px, d_files, d_back, 1, args.steps, args.warmup)
-    n_launch = launches[0]
+    ms_dev, calls_dev = timed(d_px, d_files, d_back, 1, args.steps, args.warmup)
+    n_launch = state["launches"]
     clocks = sampler.stop()
-    ms_e2e = timed(h_px, h_files, h_back, 0, args.steps, max(1, args.warmup))
-    for lv in LEVELS:
-        assert np.array_equal(h_back[lv][:frame.size].numpy(), frame.reshape(-1))
+    table_sha = state["table_sha"]
+    dev_offs = {lv: list(state["offs"][lv]) for lv in LEVELS}     # the device arena's layout (the host leg packs differently)
+    dev_sizes = {lv: list(state["sizes"][lv]) for lv in LEVELS}
+    # ---- end to end: pinned host buffers through the same C ABI calls
+    hcap = int(max(xpng_bytes.values()) * 1.05) + (1 << 20) if n else 16
+    h_files = {lv: torch.empty(hcap + 64, dtype=torch.uint8).pin_memory() for lv in LEVELS}
+    h_back = torch.empty(max(total, 16) + 64, dtype=torch.uint8).pin_memory()
+    ms_e2e, calls_e2e = timed(h_px, h_files, h_back, 0, max(1, min(args.steps, 3)), 1)
+    e2e_steps = max(1, min(args.steps, 3))
+    if n:
+        assert np.array_equal(h_back.numpy()[:total], h_px.numpy()[:total]), "e2e: decoded pixels differ"
 
-    pix_per_step = 6 * npx * world
-    value = pix_per_step / 1e6 / (ms_dev / args.steps / 1e3)
-    e2e = pix_per_step / 1e6 / (ms_e2e / args.steps / 1e3)
-    raw = frame.size
-    h2d = 3 * raw + sum(xpng_bytes.values())      # encodes upload the pixels, decodes upload the files
-    d2h = sum(xpng_bytes.values()) + 3 * raw
-
+    npx_total = F * npx_frame
+    value = 4 * npx_total / 1e6 / (ms_dev / args.steps / 1e3)
+    e2e = 4 * npx_total / 1e6 / (ms_e2e / e2e_steps / 1e3)
+    raw_shard = n * npx_frame * 3
+    # all ranks: the shard's bytes, summed by the driver's view below (rank 0 reports the whole job: every shard is the same size +-1 frame)
+    sums = torch.tensor([raw_shard, xpng_bytes[1], xpng_bytes[2]], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    raw_all, x1_all, x2_all = (int(v) for v in sums.tolist())
     if rank != 0:
+        gather.close()
         return
-    # ---- per-op breakdown and the dominant kernel (serialised profiling pass, outside the timed region)
-    breakdown = {}
-    cd.profile(True)
+    h2d = 2 * raw_all + x1_all + x2_all      # encodes upload the pixels, decodes upload the files
+    d2h = x1_all + x2_all + 2 * raw_all
+    alg = {1: raw_all + x1_all, 2: raw_all + x2_all}
+    peak, peak_src = peaks()
+
+    def table(calls):
+        out = {}
+        for k, v in sorted(calls.items()):
+            if k.startswith("gather"):
+                out[k] = {"ms": round(v * 1e3, 3)}
+            else:
+                lv = int(k[-1])
+                out[k] = {"ms": round(v * 1e3, 3), "MPix_s": round(npx_total / 1e6 / v, 1), "GB_s": round(alg[lv] / 1e9 / v, 1),
+                          "hbm_frac": round(alg[lv] / 1e9 / v / (peak * world), 4)}
+        return out
+    breakdown = {"device": table(calls_dev), "e2e": table(calls_e2e)}
+
+    # ---- level 7 on its own (stored files: a device copy)
+    if n:
+        t7 = {}
+        for _ in range(3):
+            t0 = time.perf_counter()
+            offs7, sz7 = cd.encode_raw(7, new_descs(), n, d_px.data_ptr(), total, 1, d_files[1].data_ptr(), cap, 1)
+            t1 = time.perf_counter()
+            cd.decode_raw(new_descs(True), n, d_files[1].data_ptr(), cap, 1, offs7, sz7, d_back.data_ptr(), total, 1)
+            t2 = time.perf_counter()
+            t7["enc7"] = min(t7.get("enc7", 1e9), t1 - t0); t7["dec7"] = min(t7.get("dec7", 1e9), t2 - t1)
+        npx_shard = n * npx_frame
+        breakdown["level7_rank0_shard"] = {k: {"ms": round(v * 1e3, 3), "MPix_s": round(npx_shard / 1e6 / v, 1), "GB_s": round(2 * raw_shard / 1e9 / v, 1)}
+                                           for k, v in t7.items()}
+
+    # ---- per-kernel view of one step (serialised profiling pass, outside the timed region) and the dominant kernel
     per_kernel = {}
     for lv in LEVELS:
         for what in ("enc", "dec"):
             cd.profile(True)
-            t0 = time.perf_counter()
-            d = xpng_b200.Codec.layout([frame.shape])[0]
             if what == "enc":
-                cd.encode_raw(lv, d, 1, d_px.data_ptr(), total, 1, d_files[lv].data_ptr(), cap, 1)
+                cd.encode_raw(lv, new_descs(), n, d_px.data_ptr(), total, 1, d_files[lv].data_ptr(), cap, 1)
             else:
-                d[0].w = d[0].h = 0
-                off = (C.c_uint64 * 1)(sizes[lv][0]); sz = (C.c_uint64 * 1)(sizes[lv][1])
-                cd.decode_raw(d, 1, d_files[lv].data_ptr(), cap, 1, off, sz, d_back[lv].data_ptr(), total, 1)
-            rep = cd.profile_report()
-            for k, (ms, cnt) in rep.items():
-                per_kernel[f"L{lv}.{what}.{k}"] = (ms / cnt, lv, what)
-            breakdown[f"{what}{lv}_kernel_ms"] = round(sum(ms for ms, _ in rep.values()), 3)
-    cd.profile(False)
-    for lv in LEVELS:      # un-profiled per-call times (device resident)
-        for what in ("enc", "dec"):
-            best = 1e9
-            for _ in range(3):
-                d = xpng_b200.Codec.layout([frame.shape])[0]
-                torch.cuda.synchronize(); t0 = time.perf_counter()
-                if what == "enc":
-                    cd.encode_raw(lv, d, 1, d_px.data_ptr(), total, 1, d_files[lv].data_ptr(), cap, 1)
-                else:
-                    d[0].w = d[0].h = 0
-                    off = (C.c_uint64 * 1)(sizes[lv][0]); sz = (C.c_uint64 * 1)(sizes[lv][1])
-                    cd.decode_raw(d, 1, d_files[lv].data_ptr(), cap, 1, off, sz, d_back[lv].data_ptr(), total, 1)
-                best = min(best, time.perf_counter() - t0)
-            breakdown[f"{what}{lv}_MPix_s"] = round(npx / 1e6 / best, 1)
-    top = max(per_kernel.items(), key=lambda kv: kv[1][0])
-    top_name, (top_ms, top_lv, top_what) = top
-    peak, peak_src = peaks()
-    alg_bytes = raw + xpng_bytes[top_lv] if top_lv != 7 else 2 * raw
-    achieved = alg_bytes / 1e9 / (top_ms / 1e3)
-    # DRAM traffic of that kernel from the committed `ncu --set full` capture (profiles/r01_traffic.json), per launch
+                cd.decode_raw(new_descs(True), n, d_files[lv].data_ptr(), cap, 1, (C.c_uint64 * n)(*dev_offs[lv]), (C.c_uint64 * n)(*dev_sizes[lv]),
+                              d_back.data_ptr(), total, 1)
+            for k, (ms, cnt) in cd.profile_report().items():
+                per_kernel[f"L{lv}.{what}.{k}"] = (ms, cnt, lv)
+            cd.profile(False)
+    top_name, (top_ms, top_cnt, top_lv) = max(per_kernel.items(), key=lambda kv: kv[1][0])
+    alg_shard = raw_shard + xpng_bytes[top_lv]              # algorithmic bytes of the call the kernel belongs to (rank 0's shard)
+    achieved = alg_shard / 1e9 / (top_ms / 1e3)
     traffic, traffic_src = None, None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        key = {"k_rans_v1_pair_16": "k_rans_v1_pair<16>", "k_rans_v2_pair_16": "k_rans_v2_pair<16>", "k_dec_walk_smem<0>": "k_dec_walk_smem<0>",
-               "k_dec_rans_v1_lat_values16": "k_dec_rans_v1_lat", "k_dec_rans_v2_lat": "k_dec_rans_v2_lat"}.get(top_name.split(".")[-1])
+    try:   # DRAM bytes per pixel of that kernel from the committed ncu --set full capture, scaled to this launch
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        base = top_name.split(".")[-1]
         for name, rec in tj.items():
-            if key and key in name:
-                traffic = int(rec["dram_read_bytes"] + rec["dram_write_bytes"]); traffic_src = "profiles/" + rec["report"]
+            if name == base:
+                traffic = int(rec["dram_bytes_per_pixel"] * n * npx_frame / top_cnt); traffic_src = "profiles/" + rec["report"]
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": top_name, "kernel_ms": round(top_ms, 4), "achieved": round(achieved, 2), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 5), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "dominant kernel is a serial chain fixed by the bit stream (2 rANS states per entropy block): one 4K frame is "
-                        "latency-bound, 48 warps on 148 SMs; see DESIGN.md section 3 and 6, profiles/r01_ncu_summaries.md"}
-    # ---- whole-step roofline view: algorithmic bytes of all 6 calls over the step time
-    step_bytes = sum((raw + xpng_bytes[lv]) if lv != 7 else 2 * raw for lv in LEVELS) * 2
-    breakdown["step_algorithmic_GB_s"] = round(step_bytes / 1e9 / (ms_dev / args.steps / 1e3), 2)
+    roofline = {"bound": "hbm", "kernel": top_name, "launches": top_cnt, "kernel_ms_per_launch": round(top_ms / top_cnt, 4),
+                "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_shard // top_cnt,
+                "note": "achieved = (raw + xpng bytes of the call's shard) / (sum of the kernel's launch durations in that call), CUDA events per launch "
+                        "on the launching stream (xpngb_profile, serialised pass after the timed region)"}
+    breakdown["step_algorithmic_GB_s"] = round(2 * (alg[1] + alg[2]) / 1e9 / (ms_dev / args.steps / 1e3), 1)
+    breakdown["step_hbm_frac"] = round(2 * (alg[1] + alg[2]) / 1e9 / (ms_dev / args.steps / 1e3) / (peak * world), 4)
+    breakdown["kernels_ms_rank0"] = {k: round(v[0], 3) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1][0])[:12]}
 
-    # ---- CPU baseline on a bounded sample of the same workload (rank 0, N = 1 only)
+    # ---- latency record: one 3840x2160 frame (BASELINE configs[1]) per call
+    frame4k = synth.rgb(2160, 3840, 1)
+    d4, tot4 = xpng_b200.Codec.layout([frame4k.shape])
+    cap4 = int(lib.xpngb_encode_bound(d4, 1))
+    p4 = torch.from_numpy(frame4k.reshape(-1)).to(dev); p4 = torch.cat([p4, torch.zeros(64, dtype=torch.uint8, device=dev)])
+    f4 = torch.zeros(cap4 + 64, dtype=torch.uint8, device=dev); b4 = torch.zeros(tot4 + 64, dtype=torch.uint8, device=dev)
+    lat = {}
+    for lv in (1, 2, 7):
+        be = bd = 1e9
+        for _ in range(4):
+            d = xpng_b200.Codec.layout([frame4k.shape])[0]
+            t0 = time.perf_counter()
+            o4, s4 = cd.encode_raw(lv, d, 1, p4.data_ptr(), tot4, 1, f4.data_ptr(), cap4, 1)
+            t1 = time.perf_counter()
+            d = xpng_b200.Codec.layout([frame4k.shape])[0]; d[0].w = d[0].h = 0
+            cd.decode_raw(d, 1, f4.data_ptr(), cap4, 1, o4, s4, b4.data_ptr(), tot4, 1)
+            t2 = time.perf_counter()
+            be = min(be, t1 - t0); bd = min(bd, t2 - t1)
+        assert torch.equal(b4[:tot4], p4[:tot4])
+        lat[f"enc{lv}_ms"] = round(be * 1e3, 3); lat[f"dec{lv}_ms"] = round(bd * 1e3, 3)
+    breakdown["latency_4k_frame"] = lat
+
+    # ---- the repo's own file API (xpng_store_T / xpng_load_T through tmpfs), like the reference arm does it
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        times, kind, cores, sample = reference_steps(frame, 3, 1)
-        per = sum(times) / len(times)
-        cpu = {"value": round(6 * npx / 1e6 / per, 2), "unit": "MPix/s", "cores": cores, "kind": kind, "sample": sample + "; 3 steps after 1 warm-up"}
+    if world == 1:
+        sample = synth.sintel_batch(range(SEED0, SEED0 + min(F, 16)))
+        per_step, calls = file_api_steps(C.CDLL(xpng_b200.lib_path()), sample, 2, 1, "ours")
+        breakdown["e2e_file"] = {"MPix_s": round(4 * len(sample) * npx_frame / 1e6 / per_step, 1), "frames": len(sample),
+                                 "how": "this library's xpng_store_T/xpng_load_T, one frame per call, files on tmpfs (the reference arm's own method)",
+                                 "calls": call_table(calls, len(sample) * npx_frame)}
+        if not args.no_cpu_baseline:
+            nref = min(F, 32)
+            ref_frames = synth.sintel_batch(range(SEED0, SEED0 + nref))
+            per_step, calls, kind, cores, how = reference_steps(ref_frames, 2, 1)
+            cpu = {"value": round(4 * nref * npx_frame / 1e6 / per_step, 2), "unit": "MPix/s", "cores": cores, "kind": kind,
+                   "sample": f"first {nref} frames of the batch, levels 1 and 2, encode then decode per level, {how}; 2 steps after 1 warm-up",
+                   "calls": call_table(calls, nref * npx_frame)}
 
     line = {"metric": METRIC, "value": round(value, 2), "unit": "MPix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic",
-            "config": {"workload": "configs[1]: one 3840x2160 RGB synthetic frame per GPU (seed 1+rank), levels -1/-2/-7, encode+decode",
-                       "frames_per_gpu": 1, "tiles_per_frame": 45, "l2": "flushed between timed steps (256 MiB fill)",
-                       "concurrency": "the 3 levels of a step run as 2 concurrent encode->decode pipelines: level 2 | level 1 then level 7 (one codec context and CUDA stream set per level)",
-                       "parallelism": f"frames sharded over {world} GPU(s), no collective"},
+            "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": workload_config(F, world),
             "e2e": {"value": round(e2e, 2), "unit": "MPix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": round(ms_e2e / args.steps, 4)},
+                    "ms_per_step": round(ms_e2e / e2e_steps, 4), "steps": e2e_steps},
             "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "xpng_bytes": xpng_bytes, "breakdown": breakdown}
+            "xpng_bytes": {"level1": x1_all, "level2": x2_all, "raw": raw_all}, "sizes_sha": table_sha, "breakdown": breakdown}
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        pass
+    gather.close()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=int(os.environ.get("XPNG_BENCH_FRAMES", "1000")))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
-    args.warmup = max(args.warmup, 3)
     run_ours(args, rank, world, local_rank)
     if world > 1:
         import torch.distributed as dist

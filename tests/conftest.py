@@ -9,7 +9,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 GOLD = os.path.join(ROOT, "tests", "golden")
-CORPUS = os.path.join(ROOT, "tests", "_corpus")  # git-ignored full-size corpus copies (optional)
+CORPUS = os.path.join(GOLD, "corpus")             # the reference's images/*.png (test inputs of config 0), committed
 
 
 def pytest_configure(config):
@@ -40,8 +40,7 @@ def make_case(group, name, entry):
         return load_png(os.path.join(GOLD, "crops", name))
     if group == "corpus":
         p = os.path.join(CORPUS, name)
-        if not os.path.exists(p):
-            pytest.skip("full-size corpus copy absent (tools/make_golden.py creates tests/_corpus)")
+        assert os.path.exists(p), f"{p} is missing: the config-0 corpus is a committed fixture (tools/make_golden.py)"
         return load_png(p)
     fn, args = entry["gen"]
     if fn == "full":

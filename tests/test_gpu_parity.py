@@ -274,3 +274,85 @@ def test_randomised_sweep(codec):
             assert codec.encode(lv, batch) == want, [im.shape for im in batch]
             for b, im in zip(codec.decode(want), batch):
                 assert np.array_equal(b, po.normalize(im)), im.shape
+
+
+def test_config3_golden_64_frames_pipelined(monkeypatch):
+    """BASELINE configs[2], the first 64 frames, against files written by the unmodified reference
+    (tests/golden/config3_64.json, tools/make_golden_config3.py).  The call is forced through the batch machinery:
+    several chunks on concurrent lanes (XPNGB_PIPE_MIN_MPIX), the pair-lane rANS kernels, the sorted work lists and
+    the three-tiles-per-warp walk (XPNGB_LAT_MAX_BLOCKS=0)."""
+    import hashlib
+    import json
+    import xpng_b200
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "config3_64.json")))
+    frames = synth.sintel_batch(range(1000, 1064))
+    monkeypatch.setenv("XPNGB_LAT_MAX_BLOCKS", "0")
+    monkeypatch.setenv("XPNGB_PIPE_MIN_MPIX", "20")
+    monkeypatch.setenv("XPNGB_PIPE_LANES", "4")      # 7 chunks on 4 lanes: lanes are reused within the call
+    cd = xpng_b200.Codec(0)
+    try:
+        for lv in (1, 2):
+            files = cd.encode(lv, frames)
+            for k, f in enumerate(files):
+                size, digest = gold[str(1000 + k)][str(lv)]
+                assert len(f) == size and hashlib.sha256(f).hexdigest() == digest, (lv, 1000 + k)
+            for b, im in zip(cd.decode(files), frames):
+                assert np.array_equal(b, im), lv
+    finally:
+        cd.close()
+
+
+def test_dropin_relink_of_the_reference_cli(tmp_path):
+    """The reference's own CLI source (xpng.c), compiled where it lies and linked against libxpng_b200.so instead of
+    libxpng.c / libseven.c (oracle/Makefile: _ref/xpng_dropin): .7 -> .xpng -> .7 with files identical to the reference's."""
+    dropin = os.path.join(ROOT, "oracle", "_ref", "xpng_dropin")
+    if not os.path.exists(dropin):
+        pytest.skip("oracle/_ref/xpng_dropin absent (built where /root/reference exists)")
+    px = synth.rgb(300, 410, 77)
+    src = str(tmp_path / "a.7"); po.write_7(src, px)
+    for lv in (1, 2, 7):
+        out, back = str(tmp_path / f"a{lv}.xpng"), str(tmp_path / f"b{lv}.7")
+        assert subprocess.run([dropin, f"-{lv}", src, out], capture_output=True).returncode == 0
+        assert open(out, "rb").read() == po.encode(lv, px)
+        assert subprocess.run([dropin, "-d", out, back], capture_output=True).returncode == 0
+        assert open(back, "rb").read() == open(src, "rb").read()
+
+
+def test_sharded_pool_matches_one_device():
+    """xpngb_pool_encode / xpngb_pool_decode (host threads, one context per device, no NCCL): the files and the size
+    table of a batch cut over two devices equal those of one device."""
+    import hashlib
+    import torch
+    from xpng_b200 import shard
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    frames = [synth.rgb(200 + 7 * i, 300 + 5 * i, 600 + i) for i in range(9)] + [synth.rgba(120, 90, 3)]
+    shas = []
+    for devs in ([0], [0, 1]):
+        pool = shard.Pool(devs)
+        try:
+            for lv in (1, 2):
+                files, offs, sizes = pool.encode(lv, frames)
+                assert files == [po.encode(lv, f) for f in frames]
+                shas.append((lv, hashlib.sha256(np.asarray(sizes, np.uint64).tobytes()).hexdigest()))
+                for b, im in zip(pool.decode(files), frames):
+                    assert np.array_equal(b, po.normalize(im))
+        finally:
+            pool.close()
+    assert shas[:2] == shas[2:]
+
+
+def test_single_device_pool_and_wide_one_tile_image():
+    """A one-device pool is the plain codec; a 37-row image is ONE tile 1500 pixels wide, which the staged RGB front end
+    leaves to the first-generation kernel."""
+    from xpng_b200 import shard
+    frames = [synth.rgb(37, 1500, 6), synth.rgb(1500, 37, 5), synth.rgb(64, 671, 9), synth.rgb(64, 670, 9)]
+    pool = shard.Pool([0])
+    try:
+        for lv in (1, 2):
+            files, offs, sizes = pool.encode(lv, frames)
+            assert files == [po.encode(lv, f) for f in frames]
+            for b, im in zip(pool.decode(files), frames):
+                assert np.array_equal(b, im)
+    finally:
+        pool.close()

@@ -49,7 +49,7 @@ def test_to_7_matches_pil(tmp_path, name):
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "crops", "*.png"))) +
-                         sorted(glob.glob(os.path.join(ROOT, "tests", "_corpus", "*.png"))), ids=os.path.basename)
+                         sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "corpus", "*.png"))), ids=os.path.basename)
 def test_reference_images(tmp_path, path):
     seven = str(tmp_path / "a.7")
     assert subprocess.run([SEVEN, "--to_7", path, seven]).returncode == 0

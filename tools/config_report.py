@@ -60,7 +60,7 @@ def gpu_times(imgs, level, reps=3):
 def corpus():
     from PIL import Image
     out = []
-    for p in sorted(glob.glob(os.path.join(ROOT, "tests", "_corpus", "*.png"))):
+    for p in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "corpus", "*.png"))):
         im = Image.open(p); im = im.convert("RGBA" if (im.mode in ("RGBA", "LA") or "transparency" in im.info) else "RGB")
         out.append(po.normalize(np.ascontiguousarray(np.array(im))))
     return out

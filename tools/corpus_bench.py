@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-image device times on the reference's corpus (tests/_corpus, full-size PNGs) at levels 1 and 2."""
+"""Per-image device times on the reference's corpus (tests/golden/corpus, full-size PNGs) at levels 1 and 2."""
 import os, sys, glob, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -8,7 +8,7 @@ from oracle import pyoracle as po
 from xpng_b200 import Codec
 cd = Codec(0)
 tot = {}
-for p in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "..", "tests", "_corpus", "*.png"))):
+for p in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "corpus", "*.png"))):
     im = Image.open(p); im = im.convert("RGBA" if im.mode in ("RGBA", "LA", "P") and "transparency" in im.info or im.mode == "RGBA" else "RGB")
     px = po.normalize(np.ascontiguousarray(np.array(im)))
     for lv in (1, 2):

@@ -7,7 +7,7 @@ tree for the corpus and the _ref binaries); the outputs are committed:
   tests/golden/manifest.json      per case: shape, sha256 + size of the reference .xpng per level,
                                   sha256 of the normalised pixels the reference decodes back
 
-Full-size corpus PNGs are additionally copied to tests/_corpus/ (git-ignored, travels to the GPU box).
+Full-size corpus PNGs are copied to tests/golden/corpus/ (committed: the config-0 inputs).
 """
 import hashlib, json, os, shutil, sys
 import numpy as np
@@ -92,7 +92,7 @@ def main():
     halfflat = synth.rgb(900, 900, 23); halfflat[:, :450] = [10, 200, 30]
     man["special"]["halfflat_900"] = dict(entry(halfflat), gen=["halfflat", [900, 900, 23]])
     os.makedirs(os.path.join(GOLD, "crops"), exist_ok=True)
-    corpus_dir = os.path.join(ROOT, "tests", "_corpus"); os.makedirs(corpus_dir, exist_ok=True)
+    corpus_dir = os.path.join(GOLD, "corpus"); os.makedirs(corpus_dir, exist_ok=True)
     for fn in sorted(os.listdir(REF_IMAGES)):
         if not fn.endswith(".png"):
             continue

@@ -47,7 +47,7 @@ if __name__ == "__main__":
     corpus = []
     try:
         from PIL import Image
-        for p in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "..", "tests", "_corpus", "*.png")))[:8]:
+        for p in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "corpus", "*.png")))[:8]:
             im = Image.open(p); im = im.convert("RGBA" if (im.mode in ("RGBA", "LA") or "transparency" in im.info) else "RGB")
             corpus.append(po.normalize(np.ascontiguousarray(np.array(im))))
     except Exception as e:

@@ -2,7 +2,7 @@
 """The reference's round-trip script (test.rb:1-45) re-expressed for this repo's binaries (ruby is not in the image):
 for every PNG of a directory: seven --to_7, then for each level 1, 2, 7: xpng -<level>, xpng -d, cmp; prints OK / Failed and
 the compressed size like test.rb:5-11.  JPEGs go through `xpng -3`, which is the reference's unimplemented stub (Failed).
-Usage: python tools/test_rb.py [image_dir]      (default: tests/_corpus; needs a GPU)"""
+Usage: python tools/test_rb.py [image_dir]      (default: tests/golden/corpus; needs a GPU)"""
 import filecmp, glob, os, subprocess, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SEVEN, XPNG = os.path.join(ROOT, "xpng_b200", "bin", "seven"), os.path.join(ROOT, "xpng_b200", "bin", "xpng")
@@ -11,7 +11,7 @@ def run(*a):
     return subprocess.run(a, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL).returncode == 0
 
 def main():
-    d = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "tests", "_corpus")
+    d = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "tests", "golden", "corpus")
     tmp = tempfile.mkdtemp(prefix="xpng_testrb_")
     failed = 0
     for path in sorted(glob.glob(os.path.join(d, "*"))):

@@ -141,6 +141,7 @@ struct Plan {
     std::vector<uint32_t> seg_tile;
     uint64_t px_total = 0, row_total = 0, str_total = 0, blk_total = 0;
     bool any_rgba = false;
+    bool any_wide = false;     // a tile wider than the staged front end takes (one-tile images up to 197136 x 1)
 };
 
 // Appends the tiles of one image.  base = absolute device address of its pixels.
@@ -174,6 +175,7 @@ static void plan_image(Plan& P, uint64_t base, uint64_t W, uint64_t H, uint32_t 
             P.px_total += slice; P.row_total += th;
             P.str_total += slice * sfac; P.blk_total += slice * bfac + 8192;
             for (uint32_t s = 0; s < t.nseg; s++) P.seg_tile.push_back((uint32_t)P.tiles.size());
+            if (t.w > FRONT2_MAXW) P.any_wide = true;
             P.tiles.push_back(t);
             x += tw;
         }
@@ -221,7 +223,11 @@ static int m2_encode_tiles(xpngb_ctx* ctx, const Plan& P, uint32_t ntiles, uint3
     FrontArgs fa{ d_tiles, d_seg_tile, nullptr, (const uint32_t*)ctx->costs.p, (const uint8_t*)ctx->skip.p, (SegInfo*)ctx->seginfo.p,
                   (uint8_t*)ctx->sym_area.p, (uint8_t*)ctx->bits_area.p, nullptr, (uint32_t*)ctx->hist.p, (uint16_t*)ctx->vcnt.p, 0u };
     if (ctx->root->front_v1) LAUNCH(k_front<2>, nseg, FRONT_THREADS, 0, fa);
-    else LAUNCH(k_front2<2>, nseg, FRONT_THREADS, 0, fa);      // level 2 codes RGB tiles only
+    else {                                                     // level 2 codes RGB tiles only
+        LAUNCH(k_front2<2>, nseg, FRONT_THREADS, 0, fa);
+        fa.rgba_only = 1;
+        if (P.any_wide) LAUNCH(k_front<2>, nseg, FRONT_THREADS, 0, fa);
+    }
     TileScanArgs ta{ d_tiles, (const SegInfo*)ctx->seginfo.p, (const uint32_t*)ctx->costs.p, (const uint16_t*)ctx->vcnt.p,
                      (SegPlace*)ctx->place.p, (SegPlace*)ctx->vplace.p, (uint32_t*)ctx->hist.p, (TileState*)ctx->state.p,
                      (const uint8_t*)ctx->skip.p, ntiles };
@@ -551,7 +557,7 @@ static int encode_issue(xpngb_ctx* ctx, int level, bool lat, const uint8_t* dpix
             for (uint32_t i = 0; i < n; i++) any_rgb |= pxsz[i] == 3 && mode[i] == 1;
             if (any_rgb) LAUNCH(k_front2<1>, nseg, FRONT_THREADS, 0, fa);
             fa.rgba_only = 1;
-            if (P.any_rgba) LAUNCH(k_front<1>, nseg, FRONT_THREADS, 0, fa);
+            if (P.any_rgba || P.any_wide) LAUNCH(k_front<1>, nseg, FRONT_THREADS, 0, fa);
         }
         TileScanArgs ta{ d_tiles, (const SegInfo*)ctx->seginfo.p, (const uint32_t*)ctx->costs.p, nullptr, (SegPlace*)ctx->place.p, nullptr,
                          (uint32_t*)ctx->hist.p, (TileState*)ctx->state.p, nullptr, ntiles };
@@ -1020,8 +1026,8 @@ static int decode_issue(xpngb_ctx* ctx, bool lat, xpngb_image* imgs, uint32_t n,
             LAUNCH(k_dec_rans_pair_v1_s16, pd_grid(1), PD_WARPS * 32, 0, pd_args(W, PD_S16));
             FORK_SIDE(1); side_busy[1] = true;
             LAUNCH(k_dec_rans_pair_v1_big, pd_grid(5), PD_WARPS * 32, PD_WARPS * PD_BIG_BYTES, pd_args(W, PD_BIG));
-            LAUNCH(k_pd_fill_blocks, (17u * ntiles + 3) / 4, 128, 0, fa);
             BACK_TO_MAIN();
+            LAUNCH(k_pd_fill_blocks, (17u * ntiles + 3) / 4, 128, 0, fa);   // run / raw blocks (contexts among them: before the walk)
             LAUNCH(k_dec_rans_pair_v1_s8, pd_grid(11), PD_WARPS * 32, 0, pd_args(W, PD_S8));
         }
         if (launch_walk(2)) return 1;

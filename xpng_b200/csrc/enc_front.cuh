@@ -11,6 +11,7 @@ namespace xpb {
 // for {avg2, avg2+G, grad3, grad3+G}.  grid = (ntiles, PP_SPLIT); costs must be zeroed.
 // ------------------------------------------------------------------------------------------------
 constexpr int PP_SPLIT = 4;
+constexpr uint32_t FRONT2_MAXW = 670;   // widest tile the staged RGB front end (enc_front2.cuh) takes; wider ones are one-tile images
 
 template <int PXSZ>
 __device__ __forceinline__ void predictor_cost_tile(const TileDesc& t, const uint8_t* __restrict__ px,
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(FRONT_THREADS, XPB_FRONT_MINB) k_front(FrontAr
     const uint32_t gseg = blockIdx.x, tile = A.seg_tile[gseg];
     const TileDesc t = A.tiles[tile];
     if (MODE == 2 && A.tile_skip && A.tile_skip[tile]) return;
-    if (A.rgba_only && t.pxsz != 4) return;
+    if (A.rgba_only && t.pxsz != 4 && t.w <= FRONT2_MAXW) return;
     if (MODE == 1 && t.pxsz == 4) front_segment<MODE, 4>(A, S, t, tile, gseg);
     else front_segment<MODE, 3>(A, S, t, tile, gseg);
 }

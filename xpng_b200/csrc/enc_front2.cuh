@@ -19,7 +19,8 @@
 
 namespace xpb {
 
-constexpr int F2_PADPX = 672;                       // pixels staged before the segment's first (>= 666 + 2, multiple of 16)
+constexpr int F2_PADPX = 672;                       // pixels staged before the segment's first (>= FRONT2_MAXW + 2, multiple of 16)
+static_assert(F2_PADPX >= (int)FRONT2_MAXW + 2 && F2_PADPX % 16 == 0, "staging pad");
 constexpr int F2_PIXB = (F2_PADPX + SEG) * 3;       // 14304 bytes
 static_assert(F2_PIXB >= SEG_BITS_BYTES, "the bit area reuses the staged pixels");
 
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(FRONT_THREADS, MODE == 1 ? 3 : 2) k_front2(Fro
     __shared__ __align__(16) Front2Shared S;
     const uint32_t gseg = blockIdx.x, tile = A.seg_tile[gseg];
     const TileDesc t = A.tiles[tile];
-    if (t.pxsz != 3) return;                                    // RGBA tiles: k_front
+    if (t.pxsz != 3 || t.w > FRONT2_MAXW) return;               // RGBA tiles and very wide one-tile images: k_front
     if (MODE == 2 && A.tile_skip && A.tile_skip[tile]) return;
     const uint32_t pr = pick_predictor(A.costs + 4 * tile, t.w, t.h, 3u);
     switch (pr & 3u) {
