@@ -135,7 +135,7 @@ class Codec:
 
     def profile(self, on):
         """Per-kernel CUDA-event timing (serialises launches); see profile_report()."""
-        lib().xpngb_profile(self._h, int(bool(on)))
+        lib().xpngb_profile(self._h, 3 if on == 3 else int(bool(on)))   # 3: timeline to stderr, launches not serialised
 
     def profile_report(self):
         """{kernel name: (total ms, launches)} accumulated since profile(True)."""

@@ -43,7 +43,11 @@ struct xpngb_ctx {
     cudaStream_t stream = nullptr, side[NSIDE] = {}, cur = nullptr;   // main stream, side streams for independent chains, stream of the next launch
     cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, pe0 = nullptr, pe1 = nullptr, ev_done = nullptr;
-    int profile = 0;   // 1: per-kernel CUDA-event timing accumulated (serialises the launches); 2: also print to stderr
+    int profile = 0;   // 1: per-kernel CUDA-event timing accumulated (serialises the launches); 2: also print to stderr;
+                       // 3: timeline — start/end of every launch relative to the call's start, launches NOT serialised (stderr)
+    int lane_id = 0;
+    struct TlRow { const char* name; int lane; cudaEvent_t a, b; };
+    std::vector<TlRow> tl;
     struct ProfRow { const char* name; double ms; uint32_t count; };
     std::vector<ProfRow> prof;
     char err[512] = { 0 };
@@ -81,11 +85,13 @@ struct xpngb_ctx {
 #define LAUNCH(kernel, grid, block, smem, ...)                                                      \
     do {                                                                                            \
         xpngb_ctx* r_ = ctx->root;                                                                  \
-        if (r_->profile) cudaEventRecord(ctx->pe0, ctx->cur);                                       \
+        if (r_->profile == 3) tl_mark(ctx, #kernel, 0);                                             \
+        else if (r_->profile) cudaEventRecord(ctx->pe0, ctx->cur);                                  \
         kernel<<<grid, block, smem, ctx->cur>>>(__VA_ARGS__);                                       \
         r_->launches++;                                                                             \
         CK(cudaGetLastError());                                                                     \
-        if (r_->profile) {                                                                          \
+        if (r_->profile == 3) tl_mark(ctx, #kernel, 1);                                             \
+        else if (r_->profile) {                                                                          \
             float ms_ = 0; cudaEventRecord(ctx->pe1, ctx->cur); cudaEventSynchronize(ctx->pe1);     \
             cudaEventElapsedTime(&ms_, ctx->pe0, ctx->pe1);                                         \
             prof_add(r_, #kernel, ms_);                                                             \
@@ -100,6 +106,27 @@ struct xpngb_ctx {
 #define BACK_TO_MAIN() do { ctx->cur = ctx->stream; } while (0)
 #define JOIN_SIDE(k) do { ctx->cur = ctx->stream; CK(cudaEventRecord(ctx->ev_join[k], ctx->side[k])); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0)); } while (0)
 
+// Timeline mode: two events around a launch on its own stream (no host wait); tl_dump prints them after the call.
+static void tl_mark(xpngb_ctx* ctx, const char* name, int end) {
+    xpngb_ctx* r = ctx->root;
+    if (!end) {
+        xpngb_ctx::TlRow row{ name, ctx->lane_id, nullptr, nullptr };
+        cudaEventCreate(&row.a); cudaEventCreate(&row.b);
+        cudaEventRecord(row.a, ctx->cur);
+        r->tl.push_back(row);
+    } else cudaEventRecord(r->tl.back().b, ctx->cur);
+}
+static void tl_dump(xpngb_ctx* ctx, const char* what) {
+    if (ctx->profile != 3) return;
+    cudaDeviceSynchronize();
+    for (auto& row : ctx->tl) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, ctx->ev0, row.a); cudaEventElapsedTime(&b, ctx->ev0, row.b);
+        fprintf(stderr, "TL %s %d %s %.3f %.3f\n", what, row.lane, row.name, a, b);
+        cudaEventDestroy(row.a); cudaEventDestroy(row.b);
+    }
+    ctx->tl.clear();
+}
 static void prof_add(xpngb_ctx* ctx, const char* name, float ms) {
     for (auto& r : ctx->prof) if (!strcmp(r.name, name)) { r.ms += ms; r.count++; return; }
     ctx->prof.push_back({ name, ms, 1 });
@@ -320,6 +347,7 @@ static xpngb_ctx* lane_get(xpngb_ctx* root, uint32_t i) {
         xpngb_ctx* l = lane_new(root->device, root);
         if (!l) return nullptr;
         root->lanes.push_back(l);
+        l->lane_id = (int)root->lanes.size();
     }
     return root->lanes[i - 1];
 }
@@ -332,7 +360,7 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     if (cudaSetDevice(device) != cudaSuccess) return 1;
     xpngb_ctx* ctx = lane_new(device, nullptr);
     if (!ctx) return 1;
-    if (const char* e = getenv("XPNGB_PROFILE")) ctx->profile = atoi(e) ? 2 : 0;
+    if (const char* e = getenv("XPNGB_PROFILE")) ctx->profile = atoi(e) == 3 ? 3 : (atoi(e) ? 2 : 0);
     if (const char* e = getenv("XPNGB_CHUNK_MPIX")) { const long v = atol(e); if (v > 0) ctx->max_chunk_px = (uint64_t)v << 20; }
     if (const char* e = getenv("XPNGB_PIPE_LANES")) { const long v = atol(e); if (v > 0 && v <= 64) ctx->pipe_lanes = (uint32_t)v; }
     if (const char* e = getenv("XPNGB_PIPE_MIN_MPIX")) { const long v = atol(e); if (v > 0) ctx->pipe_min_px = (uint64_t)v << 20; }
@@ -368,7 +396,7 @@ extern "C" float xpngb_last_kernel_ms(const xpngb_ctx* ctx) { return ctx ? ctx->
 extern "C" uint32_t xpngb_last_launches(const xpngb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" void* xpngb_stream(const xpngb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
-extern "C" void xpngb_profile(xpngb_ctx* ctx, int on) { if (ctx) { ctx->profile = on ? (ctx->profile > 1 ? 2 : 1) : 0; ctx->prof.clear(); } }
+extern "C" void xpngb_profile(xpngb_ctx* ctx, int on) { if (ctx) { ctx->profile = on == 3 ? 3 : (on ? (ctx->profile == 2 ? 2 : 1) : 0); ctx->prof.clear(); } }
 extern "C" uint32_t xpngb_profile_report(const xpngb_ctx* ctx, char* buf, uint32_t cap) {
     uint32_t n = 0;
     if (!ctx || !buf || !cap) return 0;
@@ -733,6 +761,7 @@ extern "C" int xpngb_encode(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !rc) { snprintf(ctx->err, sizeof ctx->err, "device error: %s", cudaGetErrorString(cudaGetLastError())); rc = 1; }
     if (rc) { for (xpngb_ctx* l : ctx->lanes) cudaStreamSynchronize(l->stream); return 1; }
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    tl_dump(ctx, "enc");
     return 0;
 }
 
@@ -1161,6 +1190,7 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
     cudaStreamSynchronize(ctx->stream);
     if (rc) return 1;
     CK(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    tl_dump(ctx, "dec");
     return 0;
 }
 
