@@ -6,4 +6,10 @@ This package is the thin ctypes mirror used by the tests and bench.py; it never 
 implementation: importing `codec` without the built library, or creating a Codec without a CUDA
 device, raises.
 """
+import os as _os
+
+# A batch call keeps up to 24 CUDA streams busy; with the driver's default of 8 hardware queues they would wait on each
+# other.  The driver reads this when CUDA initialises, so it must be in place before the process's first CUDA call.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 from .codec import Codec, LibraryMissing, lib, lib_path, xpng_store, xpng_load, load_7, store_7  # noqa: F401

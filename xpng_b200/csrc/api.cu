@@ -22,6 +22,7 @@
 #include "enc_back.cuh"
 #include "enc_m2.cuh"
 #include "enc_rans_lat.cuh"
+#include "enc_order.cuh"
 #include "dec_m1.cuh"
 #include "dec_back.cuh"
 #include "dec_rans_lat.cuh"
@@ -41,6 +42,10 @@ struct xpngb_ctx {
     std::vector<xpngb_ctx*> lanes;             // root only: further lanes (lane 0 is the root itself), created on demand
     static constexpr int NSIDE = 5;
     cudaStream_t stream = nullptr, side[NSIDE] = {}, cur = nullptr;   // main stream, side streams for independent chains, stream of the next launch
+    cudaStream_t hi = nullptr;                 // high-priority twin of the main stream: serial-chain kernels (LAUNCH_HI)
+    cudaEvent_t ev_hi = nullptr;
+    bool enc_sorted = true;                    // root: XPNGB_ENC_SORT=0: pair encoders take blocks in tile order (A/B)
+    bool use_prio = true;                      // root: XPNGB_PRIO=0 switches the priorities off (A/B)
     cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, pe0 = nullptr, pe1 = nullptr, ev_done = nullptr;
     int profile = 0;   // 1: per-kernel CUDA-event timing accumulated (serialises the launches); 2: also print to stderr;
@@ -61,10 +66,11 @@ struct xpngb_ctx {
     uint32_t direct_max_tiles = 148;  // level-2 decode: tiles per call up to which the 64 KiB direct tables are used (3 chains per SM stay resident)
     uint32_t v2_direct_max_tiles = ~0u;  // level-1 decode: same trade for the 16 KiB context tables
     uint32_t unr_multi_max_tiles = 592, unr_force = 0;   // un-predict: tiles per call up to which a tile gets 8 warps; XPNGB_UNR_NW forces a variant (A/B)
-    uint32_t lat_max_blocks = 32768;  // entropy blocks per call up to which the warp-per-block (latency) kernels are used (measured crossover, profiles/)
+    uint32_t lat_max_blocks = 32768;  // decode: entropy blocks per call up to which the warp-per-block (latency) kernels are used (measured crossover, profiles/)
+    uint32_t enc_lat_max_blocks = ~0u; // encode: the pair-lane encoders serve every batch size (chunks in flight keep their launches resident)
     // device scratch
     DevBuf pixels, norm, files, arena, tiles, imgs, seg_tile, costs, hist, seginfo, place, vplace, vcnt, sym_area,
-        bits_area, alpha, streams, blocks, state, outs, flags, skip, dimgs, dtiles, plane, nlseq, rowcnt, rowbits,
+        bits_area, alpha, streams, blocks, state, outs, flags, skip, dimgs, dtiles, plane, nlseq, rowcnt, rowbits, eord,
         rows, edge, errflag, hdr, offs, m2a, m2b, tclass, tabs, ccnt, cbit, resv, oriented, odesc, pdw;
     PinBuf pin_a, pin_b, pin_o;   // pin_o: orientation descriptors (their upload may still be in flight when an encode reuses pin_a)
 };
@@ -101,8 +107,34 @@ struct xpngb_ctx {
 
 // Independent serial chains (e.g. the value-stream blocks of level 2 while the context streams are walked)
 // run on the side stream: FORK makes it wait for everything launched so far, JOIN makes the main stream wait for it.
+// Chain kernels (rANS recurrences, context walks, the tiny serial scans between them) keep a few warps busy for a long
+// time; the data-parallel kernels of the other chunks in flight fill the machine.  The block scheduler serves streams
+// of higher priority first, so chains go to high-priority streams: their CTAs become resident as soon as they are
+// launched instead of queueing behind hundreds of thousands of front-end CTAs.
+static cudaStream_t prio_stream(const xpngb_ctx* ctx) {
+    cudaStream_t s = nullptr;
+    int lo = 0, hi = 0;
+    if (ctx->root->use_prio && cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess && hi != lo) cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi);
+    else cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    return s;
+}
+static cudaStream_t side_of(xpngb_ctx* ctx, int k) {
+    if (!ctx->side[k]) ctx->side[k] = prio_stream(ctx);   // side streams only ever carry chains
+    return ctx->side[k];
+}
+#define LAUNCH_HI(kernel, grid, block, smem, ...)                                                   \
+    do {                                                                                            \
+        cudaStream_t base_ = ctx->cur;                                                              \
+        const bool tw_ = base_ == ctx->stream && ctx->root->use_prio && (ctx->root->profile == 0 || ctx->root->profile == 3);       \
+        if (tw_) {                                                                                  \
+            if (!ctx->hi) ctx->hi = prio_stream(ctx);                                               \
+            CK(cudaEventRecord(ctx->ev_hi, base_)); CK(cudaStreamWaitEvent(ctx->hi, ctx->ev_hi, 0)); ctx->cur = ctx->hi; \
+        }                                                                                           \
+        LAUNCH(kernel, grid, block, smem, __VA_ARGS__);                                             \
+        if (tw_) { CK(cudaEventRecord(ctx->ev_hi, ctx->hi)); CK(cudaStreamWaitEvent(base_, ctx->ev_hi, 0)); ctx->cur = base_; } \
+    } while (0)
 #define FORK_SIDE(k) FORK_FROM(ctx->stream, k)
-#define FORK_FROM(src, k) do { CK(cudaEventRecord(ctx->ev_fork, (src))); CK(cudaStreamWaitEvent(ctx->side[k], ctx->ev_fork, 0)); ctx->cur = ctx->side[k]; } while (0)
+#define FORK_FROM(src, k) do { CK(cudaEventRecord(ctx->ev_fork, (src))); CK(cudaStreamWaitEvent(side_of(ctx, k), ctx->ev_fork, 0)); ctx->cur = ctx->side[k]; } while (0)
 #define BACK_TO_MAIN() do { ctx->cur = ctx->stream; } while (0)
 #define JOIN_SIDE(k) do { ctx->cur = ctx->stream; CK(cudaEventRecord(ctx->ev_join[k], ctx->side[k])); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[k], 0)); } while (0)
 
@@ -258,7 +290,7 @@ static int m2_encode_tiles(xpngb_ctx* ctx, const Plan& P, uint32_t ntiles, uint3
     TileScanArgs ta{ d_tiles, (const SegInfo*)ctx->seginfo.p, (const uint32_t*)ctx->costs.p, (const uint16_t*)ctx->vcnt.p,
                      (SegPlace*)ctx->place.p, (SegPlace*)ctx->vplace.p, (uint32_t*)ctx->hist.p, (TileState*)ctx->state.p,
                      (const uint8_t*)ctx->skip.p, ntiles };
-    LAUNCH(k_tile_scan<2>, (ntiles + 3) / 4, 128, 0, ta);
+    LAUNCH_HI(k_tile_scan<2>, (ntiles + 3) / 4, 128, 0, ta);
     CompactArgs ca{ d_tiles, d_seg_tile, (const SegInfo*)ctx->seginfo.p, (const SegPlace*)ctx->place.p, (const SegPlace*)ctx->vplace.p,
                     (const uint16_t*)ctx->vcnt.p, (const TileState*)ctx->state.p, (const uint8_t*)ctx->sym_area.p,
                     (const uint8_t*)ctx->bits_area.p, (uint8_t*)ctx->streams.p, (const uint8_t*)ctx->skip.p };
@@ -268,17 +300,25 @@ static int m2_encode_tiles(xpngb_ctx* ctx, const Plan& P, uint32_t ntiles, uint3
                    (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->blocks.p, (uint32_t*)ctx->tabs.p, ntiles, 0, 17, 0, 0 };
     if (lat) {
         auto k_rans_v1_pair_16 = k_rans_v1_pair<16>; auto k_rans_v1_pair_256 = k_rans_v1_pair<256>;
+        const uint32_t ecap = 17u * ntiles;
+        if (ctx->root->enc_sorted) {                   // blocks by decreasing length, one list per table size (enc_order.cuh)
+            ENSURE(eord, (size_t)(2 * ecap + 2) * 4);
+            uint32_t* eo = (uint32_t*)ctx->eord.p;
+            LAUNCH_HI(k_enc_order, 1, 1024, 0, EncOrderArgs{ d_tiles, (const TileState*)ctx->state.p, (const uint8_t*)ctx->tclass.p, ntiles, 2u, eo + 2, eo, ecap });
+            ra.order = eo + 2; ra.total = eo;
+        }
         // alphabets above 16 symbols and the grey candidates go to a side stream that forks BEFORE the main launch but is
         // fed AFTER it: the small-alphabet kernel holds the longest chains, and in a batch its CTAs must be placed first
         // (the 98 KiB CTAs of the other kernel would otherwise take the shared memory and delay them)
         FORK_SIDE(0);
         BACK_TO_MAIN();
-        LAUNCH(k_rans_v1_pair_16, (17 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 17 * PAIR_BLK * 24, ra);
+        LAUNCH_HI(k_rans_v1_pair_16, (17 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 17 * PAIR_BLK * 24, ra);
         ctx->cur = ctx->side[0];
         RansV1Args rb = ra; rb.c0 = 9; rb.nc = 8; rb.nmin = 16;
-        LAUNCH(k_rans_v1_pair_256, (8 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, rb);
-        rb.c0 = 0; rb.nc = 4; rb.nmin = 0; rb.grey = 1;
-        LAUNCH(k_rans_v1_pair_256, (4 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, rb);
+        if (ra.order) { rb.order = ra.order + ecap; rb.total = ra.total + 1; }
+        LAUNCH_HI(k_rans_v1_pair_256, (8 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, rb);
+        rb.c0 = 0; rb.nc = 4; rb.nmin = 0; rb.grey = 1; rb.order = nullptr; rb.total = nullptr;
+        LAUNCH_HI(k_rans_v1_pair_256, (4 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, rb);
         JOIN_SIDE(0);
     } else {
     auto k_rans_v1_lane_16 = k_rans_v1<16, 128>; auto k_rans_v1_lane_256 = k_rans_v1<256, 32>;
@@ -288,7 +328,7 @@ static int m2_encode_tiles(xpngb_ctx* ctx, const Plan& P, uint32_t ntiles, uint3
     ra.c0 = 0; ra.nc = 4; ra.nmin = 0; ra.grey = 1;
     LAUNCH(k_rans_v1_lane_256, (4 * ntiles + 31) / 32, 32, 256 * 32 * 16, ra);
     }
-    LAUNCH(k_m2_finish, (ntiles + 127) / 128, 128, 0, d_tiles, (const uint8_t*)ctx->tclass.p, (TileState*)ctx->state.p, ntiles);
+    LAUNCH_HI(k_m2_finish, (ntiles + 127) / 128, 128, 0, d_tiles, (const uint8_t*)ctx->tclass.p, (TileState*)ctx->state.p, ntiles);
     return 0;
 }
 // CTAs per tile for the assembly kernels: a single frame has fewer tiles than SMs, so each tile's copies are sliced
@@ -312,12 +352,13 @@ static void lane_free(xpngb_ctx* ctx) {
                       &ctx->streams, &ctx->blocks, &ctx->state, &ctx->outs, &ctx->flags, &ctx->skip, &ctx->dimgs, &ctx->dtiles,
                       &ctx->plane, &ctx->nlseq, &ctx->rowcnt, &ctx->rowbits, &ctx->rows, &ctx->edge, &ctx->errflag, &ctx->hdr,
                       &ctx->offs, &ctx->m2a, &ctx->m2b, &ctx->tclass, &ctx->tabs, &ctx->ccnt, &ctx->cbit, &ctx->resv, &ctx->oriented,
-                      &ctx->odesc, &ctx->pdw };
+                      &ctx->odesc, &ctx->pdw, &ctx->eord };
     for (DevBuf* b : all) if (b->p) cudaFree(b->p);
     if (ctx->pin_a.p) cudaFreeHost(ctx->pin_a.p);
     if (ctx->pin_b.p) cudaFreeHost(ctx->pin_b.p);
     if (ctx->pin_o.p) cudaFreeHost(ctx->pin_o.p);
-    cudaEvent_t evs[] = { ctx->ev0, ctx->ev1, ctx->ev_fork, ctx->pe0, ctx->pe1, ctx->ev_done };
+    if (ctx->hi) { cudaStreamSynchronize(ctx->hi); cudaStreamDestroy(ctx->hi); }
+    cudaEvent_t evs[] = { ctx->ev0, ctx->ev1, ctx->ev_fork, ctx->pe0, ctx->pe1, ctx->ev_done, ctx->ev_hi };
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     for (int k = 0; k < xpngb_ctx::NSIDE; k++) { if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]); if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -331,11 +372,11 @@ static xpngb_ctx* lane_new(int device, xpngb_ctx* root) {
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_hi, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
               cudaEventCreate(&ctx->pe0) == cudaSuccess && cudaEventCreate(&ctx->pe1) == cudaSuccess;
-    for (int k = 0; ok && k < xpngb_ctx::NSIDE; k++)
-        ok = cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; ok && k < xpngb_ctx::NSIDE; k++)   // side streams are created on first use (side_of): the device has at most
+        ok = cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming) == cudaSuccess;   // 32 hardware queues, unused streams would alias used ones
     if (!ok) { lane_free(ctx); return nullptr; }
     ctx->cur = ctx->stream;
     return ctx;
@@ -355,6 +396,10 @@ static xpngb_ctx* lane_get(xpngb_ctx* root, uint32_t i) {
 extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     if (!out) return 1;
     *out = nullptr;
+    // a call keeps up to pipe_lanes x 3 streams busy; the driver's default of 8 hardware queues would make them wait on each
+    // other (false dependencies).  Read by the driver when it initialises, so this only acts in a process that has not
+    // touched CUDA yet; hosts that initialise CUDA first set it themselves.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return 1;
     if (cudaSetDevice(device) != cudaSuccess) return 1;
@@ -367,11 +412,14 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     { auto k_big = k_rans_v2<256, 32>; cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 16); }
     m2_set_attributes();
     if (const char* e = getenv("XPNGB_LAT_MAX_BLOCKS")) ctx->lat_max_blocks = (uint32_t)atol(e);
+    if (const char* e = getenv("XPNGB_ENC_LAT_MAX_BLOCKS")) ctx->enc_lat_max_blocks = (uint32_t)atol(e);
     if (const char* e = getenv("XPNGB_V2_DIRECT_MAX_TILES")) ctx->v2_direct_max_tiles = (uint32_t)atol(e);
     if (const char* e = getenv("XPNGB_WALK")) { ctx->walk_global = !strcmp(e, "global"); ctx->walk_ring = !strcmp(e, "ring"); }
     if (const char* e = getenv("XPNGB_DIRECT_MAX_TILES")) ctx->direct_max_tiles = (uint32_t)atol(e);
     if (const char* e = getenv("XPNGB_UNR_NW")) ctx->unr_force = (uint32_t)atol(e);
     if (const char* e = getenv("XPNGB_FRONT")) ctx->front_v1 = atoi(e) == 1;
+    if (const char* e = getenv("XPNGB_PRIO")) ctx->use_prio = atoi(e) != 0;
+    if (const char* e = getenv("XPNGB_ENC_SORT")) ctx->enc_sorted = atoi(e) != 0;
     { auto p = k_rans_v2_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * PAIR_BLK * 24); }
     { auto p = k_rans_v1_pair<256>; cudaFuncSetAttribute(p, cudaFuncAttributeMaxDynamicSharedMemorySize, 257 * PAIR_BLK * 24); }
     cudaFuncSetAttribute(k_dec_unpredict_rows<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2 * 32 * UNR_PITCH);
@@ -589,7 +637,7 @@ static int encode_issue(xpngb_ctx* ctx, int level, bool lat, const uint8_t* dpix
         }
         TileScanArgs ta{ d_tiles, (const SegInfo*)ctx->seginfo.p, (const uint32_t*)ctx->costs.p, nullptr, (SegPlace*)ctx->place.p, nullptr,
                          (uint32_t*)ctx->hist.p, (TileState*)ctx->state.p, nullptr, ntiles };
-        LAUNCH(k_tile_scan<1>, (ntiles + 3) / 4, 128, 0, ta);
+        LAUNCH_HI(k_tile_scan<1>, (ntiles + 3) / 4, 128, 0, ta);
         CompactArgs ca{ d_tiles, d_seg_tile, (const SegInfo*)ctx->seginfo.p, (const SegPlace*)ctx->place.p, nullptr, nullptr,
                         (const TileState*)ctx->state.p, (const uint8_t*)ctx->sym_area.p, (const uint8_t*)ctx->bits_area.p,
                         (uint8_t*)ctx->streams.p, nullptr };
@@ -598,15 +646,23 @@ static int encode_issue(xpngb_ctx* ctx, int level, bool lat, const uint8_t* dpix
                        (const uint8_t*)ctx->alpha.p, (uint8_t*)ctx->blocks.p, ntiles, 0, 9 };
         if (lat) {
             auto k_rans_v2_pair_16 = k_rans_v2_pair<16>; auto k_rans_v2_pair_256 = k_rans_v2_pair<256>;
+            const uint32_t ecap = 10u * ntiles;
+            if (ctx->root->enc_sorted) {               // blocks by decreasing length (enc_order.cuh)
+                ENSURE(eord, (size_t)(2 * ecap + 2) * 4);
+                uint32_t* eo = (uint32_t*)ctx->eord.p;
+                LAUNCH_HI(k_enc_order, 1, 1024, 0, EncOrderArgs{ d_tiles, (const TileState*)ctx->state.p, nullptr, ntiles, 1u, eo + 2, eo, ecap });
+                ra.order = eo + 2; ra.total = eo;
+            }
             if (P.any_rgba) {                          // the alpha blocks are independent of the context blocks: side stream
                 FORK_SIDE(0);                          // forks before, is fed after the main launch (see m2_encode_tiles)
                 BACK_TO_MAIN();
             }
-            LAUNCH(k_rans_v2_pair_16, (9 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 17 * PAIR_BLK * 24, ra);
+            LAUNCH_HI(k_rans_v2_pair_16, (9 * ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 17 * PAIR_BLK * 24, ra);
             if (P.any_rgba) {
                 RansV2Args rb = ra; rb.c0 = 9; rb.nc = 1;
+                if (ra.order) { rb.order = ra.order + ecap; rb.total = ra.total + 1; }
                 ctx->cur = ctx->side[0];
-                LAUNCH(k_rans_v2_pair_256, (ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, rb);
+                LAUNCH_HI(k_rans_v2_pair_256, (ntiles + PAIR_BLK - 1) / PAIR_BLK, 32, 257 * PAIR_BLK * 24, rb);
                 JOIN_SIDE(0);
             }
         } else {
@@ -621,8 +677,8 @@ static int encode_issue(xpngb_ctx* ctx, int level, bool lat, const uint8_t* dpix
     if (any2) {
         if (m2_encode_tiles(ctx, P, ntiles, nseg, lat)) return 1;
     }
-    LAUNCH(k_image_sizes, (n + 127) / 128, 128, 0, d_imgs, d_tiles, (TileState*)ctx->state.p, (ImageOut*)ctx->outs.p, n);
-    LAUNCH(k_image_offsets, 1, 1, 0, (ImageOut*)ctx->outs.p, n, C.out_base);
+    LAUNCH_HI(k_image_sizes, (n + 127) / 128, 128, 0, d_imgs, d_tiles, (TileState*)ctx->state.p, (ImageOut*)ctx->outs.p, n);
+    LAUNCH_HI(k_image_offsets, 1, 1, 0, (ImageOut*)ctx->outs.p, n, C.out_base);
     {
         AssembleArgs aa{ d_imgs, d_tiles, (const TileState*)ctx->state.p, (const ImageOut*)ctx->outs.p, (const SegInfo*)ctx->seginfo.p,
                          (const SegPlace*)ctx->place.p, nullptr, (const uint8_t*)ctx->bits_area.p, (const uint8_t*)ctx->blocks.p, dout };
@@ -708,7 +764,7 @@ extern "C" int xpngb_encode(xpngb_ctx* ctx, int level, xpngb_image* imgs, uint32
     uint64_t tiles_est = 0;
     for (uint32_t i = 0; i < n; i++) tiles_est += (imgs[i].w * imgs[i].h + TILE_AREA - 1) / TILE_AREA;
     // kernel family by the size of the CALL (what is in flight at once), not of a chunk
-    const bool lat = (level == 2 ? 17 * tiles_est <= (uint64_t)ctx->lat_max_blocks * 5 / 2 : 9 * tiles_est <= ctx->lat_max_blocks);
+    const bool lat = (level == 2 ? 17 * tiles_est <= (uint64_t)ctx->enc_lat_max_blocks * 5 / 2 : 9 * tiles_est <= ctx->enc_lat_max_blocks);
     std::vector<EncChunk> chunks(nchunks);
     uint64_t host_packed = 0;   // host output: files are packed across chunks
     int rc = 0;
@@ -932,7 +988,7 @@ static int decode_issue(xpngb_ctx* ctx, bool lat, xpngb_image* imgs, uint32_t n,
         ENSURE(ccnt, (size_t)nseg * 9 * 4); ENSURE(cbit, (size_t)nseg * 4); ENSURE(resv, P.px_total * 4);
         if (P.any_rgba) { ENSURE(alpha, P.px_total); ENSURE(plane, P.px_total); }
         if (!lat) { ENSURE(pdw, 2 * pdw_bytes(pd_cap)); CK(cudaMemsetAsync(ctx->pdw.p, 0, 2 * pdw_bytes(pd_cap), ctx->stream)); }
-        LAUNCH(k_dec_tile_offsets, (n + 127) / 128, 128, 0, d_imgs, din, d_dt, n, d_err);
+        LAUNCH_HI(k_dec_tile_offsets, (n + 127) / 128, 128, 0, d_imgs, din, d_dt, n, d_err);
     }
     // Stream plan of one chunk.  Main stream: the level-2 family (or the only family).  side[2]: the level-1 family
     // when both are present (config 0: the corpus mixes RGB and RGBA files).  side[0], side[1]: level-2
@@ -945,28 +1001,28 @@ static int decode_issue(xpngb_ctx* ctx, bool lat, xpngb_image* imgs, uint32_t n,
         WalkArgs wa{ d_tiles, d_imgs, d_dt, (const uint8_t*)ctx->streams.p, (uint8_t*)ctx->nlseq.p, ntiles, mode };
         if (!lat && !ctx->root->walk_ring && !ctx->root->walk_global) {   // batches: three tiles per warp, longest tiles first
             const PdWork& W = Wl[mode];
-            LAUNCH(k_dec_walk3<2>, (ntiles + 5) / 6, 64, 0, wa, (const uint32_t*)(W.order + (size_t)PD_WALK * W.cap), (const uint32_t*)(W.total + PD_WALK));
+            LAUNCH_HI(k_dec_walk3<2>, (ntiles + 5) / 6, 64, 0, wa, (const uint32_t*)(W.order + (size_t)PD_WALK * W.cap), (const uint32_t*)(W.total + PD_WALK));
             return 0;
         }
         // the shared-memory walk only pays when every tile's CTA of the CALL is resident at once (no waves): 227 KB per SM, 148 SMs
         const uint32_t resident = 148u * ((227u * 1024u) / (wsm + 1024u));
         xpngb_ctx* r = ctx->root;
-        if (call_tiles <= resident && maxpx <= WALK_SMEM_MAX_SYMS && !r->walk_ring && !r->walk_global) LAUNCH(k_dec_walk_smem<0>, ntiles, 32, wsm, wa);
+        if (call_tiles <= resident && maxpx <= WALK_SMEM_MAX_SYMS && !r->walk_ring && !r->walk_global) LAUNCH_HI(k_dec_walk_smem<0>, ntiles, 32, wsm, wa);
         else if (r->walk_global) {                     // XPNGB_WALK=global: the older variant with refills straight from global memory
-            if (ntiles <= 592) LAUNCH(k_dec_walk_lat<1>, ntiles, 32, 0, wa);
-            else LAUNCH(k_dec_walk_lat<4>, (ntiles + 3) / 4, 128, 0, wa);
+            if (ntiles <= 592) LAUNCH_HI(k_dec_walk_lat<1>, ntiles, 32, 0, wa);
+            else LAUNCH_HI(k_dec_walk_lat<4>, (ntiles + 3) / 4, 128, 0, wa);
         }
-        else if (call_tiles <= 592) LAUNCH(k_dec_walk_ring<1>, ntiles, 32, 0, wa);
-        else LAUNCH(k_dec_walk_ring<4>, (ntiles + 3) / 4, 128, 0, wa);
+        else if (call_tiles <= 592) LAUNCH_HI(k_dec_walk_ring<1>, ntiles, 32, 0, wa);
+        else LAUNCH_HI(k_dec_walk_ring<4>, (ntiles + 3) / 4, 128, 0, wa);
         return 0;
     };
     // pair decoders of one level family: work lists, run / raw fills, then one launch per class
     auto pd_lists = [&](uint32_t mode, PdWork& W) -> int {
         W = pdw_at((uint8_t*)ctx->pdw.p + (mode == 1 ? 0 : pdw_bytes(pd_cap)), pd_cap);
         const unsigned g = (17u * ntiles + 255) / 256;
-        LAUNCH(k_pd_count, g, 256, 0, d_tiles, d_imgs, (const DecTile*)d_dt, ntiles, mode, W);
-        LAUNCH(k_pd_scan, PD_NCLASS, 1024, 0, W);
-        LAUNCH(k_pd_fill, g, 256, 0, d_tiles, d_imgs, (const DecTile*)d_dt, ntiles, mode, W);
+        LAUNCH_HI(k_pd_count, g, 256, 0, d_tiles, d_imgs, (const DecTile*)d_dt, ntiles, mode, W);
+        LAUNCH_HI(k_pd_scan, PD_NCLASS, 1024, 0, W);
+        LAUNCH_HI(k_pd_fill, g, 256, 0, d_tiles, d_imgs, (const DecTile*)d_dt, ntiles, mode, W);
         return 0;
     };
     auto pd_args = [&](const PdWork& W, int cls) {
@@ -975,9 +1031,9 @@ static int decode_issue(xpngb_ctx* ctx, bool lat, xpngb_image* imgs, uint32_t n,
     auto pd_grid = [&](uint32_t per_tile) { return (unsigned)(((uint64_t)per_tile * ntiles + PD_BLK * PD_WARPS - 1) / (PD_BLK * PD_WARPS)); };
     if (any1) {
         const bool own_stream = any2;                   // level-1 family next to a level-2 family
-        cudaStream_t f1 = own_stream ? ctx->side[2] : ctx->stream;
+        cudaStream_t f1 = own_stream ? side_of(ctx, 2) : ctx->stream;
         if (own_stream) { FORK_SIDE(2); side_busy[2] = true; }
-        LAUNCH(k_dec_parse_m1, (ntiles + 127) / 128, 128, 0, d_tiles, d_imgs, din, d_dt, ntiles, d_err);
+        LAUNCH_HI(k_dec_parse_m1, (ntiles + 127) / 128, 128, 0, d_tiles, d_imgs, din, d_dt, ntiles, d_err);
         RansDecArgs ra{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, (uint8_t*)ctx->alpha.p, ntiles, 0, 9, d_err };
         AlphaArgs al{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->alpha.p, (uint8_t*)ctx->plane.p, (uint32_t*)ctx->rowcnt.p };
         if (lat) {
@@ -985,34 +1041,34 @@ static int decode_issue(xpngb_ctx* ctx, bool lat, xpngb_image* imgs, uint32_t n,
                 FORK_FROM(f1, 3); side_busy[3] = true;
                 RansDecArgs rb = ra; rb.c0 = 9; rb.nc = 1;
                 auto k_dec_rans_v2_lat_alpha = k_dec_rans_v2_lat;
-                LAUNCH(k_dec_rans_v2_lat_alpha, ntiles, 32, lat_smem(LUT_TWO_15), rb, LUT_TWO_15);
+                LAUNCH_HI(k_dec_rans_v2_lat_alpha, ntiles, 32, lat_smem(LUT_TWO_15), rb, LUT_TWO_15);
                 LAUNCH(k_dec_alpha, ntiles, 256, 0, al);
                 LAUNCH(k_dec_rows_rgba, ntiles, 32, 0, d_tiles, d_imgs, (const DecTile*)d_dt, (const uint32_t*)ctx->rowcnt.p, (RowInfo*)ctx->rows.p);
             }
             ctx->cur = f1;
             const uint32_t lut12 = call_tiles <= ctx->root->v2_direct_max_tiles ? LUT_ONE_12 : LUT_TWO_12;
-            LAUNCH(k_dec_rans_v2_lat, 9 * ntiles, 32, lat_smem(lut12), ra, lut12);
+            LAUNCH_HI(k_dec_rans_v2_lat, 9 * ntiles, 32, lat_smem(lut12), ra, lut12);
         } else {
             PdWork& W = Wl[1];
             if (pd_lists(1, W)) return 1;
             PdFillArgs fa{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, (uint8_t*)ctx->alpha.p, ntiles, 1 };
-            LAUNCH(k_pd_fill_blocks, (17u * ntiles + 3) / 4, 128, 0, fa);
+            LAUNCH_HI(k_pd_fill_blocks, (17u * ntiles + 3) / 4, 128, 0, fa);
             if (P.any_rgba) {
                 FORK_FROM(f1, 3); side_busy[3] = true;
                 auto k_dec_rans_pair_v2_alpha = k_dec_rans_pair<2, 0>;
-                LAUNCH(k_dec_rans_pair_v2_alpha, pd_grid(1), PD_WARPS * 32, PD_WARPS * PD_BIG_BYTES, pd_args(W, PD_BIG));
+                LAUNCH_HI(k_dec_rans_pair_v2_alpha, pd_grid(1), PD_WARPS * 32, PD_WARPS * PD_BIG_BYTES, pd_args(W, PD_BIG));
                 LAUNCH(k_dec_alpha, ntiles, 256, 0, al);
                 LAUNCH(k_dec_rows_rgba, ntiles, 32, 0, d_tiles, d_imgs, (const DecTile*)d_dt, (const uint32_t*)ctx->rowcnt.p, (RowInfo*)ctx->rows.p);
             }
             ctx->cur = f1;
             auto k_dec_rans_pair_v2_ctx = k_dec_rans_pair<2, 8>;
-            LAUNCH(k_dec_rans_pair_v2_ctx, pd_grid(9), PD_WARPS * 32, 0, pd_args(W, PD_S8));
+            LAUNCH_HI(k_dec_rans_pair_v2_ctx, pd_grid(9), PD_WARPS * 32, 0, pd_args(W, PD_S8));
         }
         if (launch_walk(1)) return 1;
         BACK_TO_MAIN();
     }
     if (any2) {
-        LAUNCH(k_dec_parse_m2, (ntiles + 127) / 128, 128, 0, d_tiles, d_imgs, din, d_dt, ntiles, d_err);
+        LAUNCH_HI(k_dec_parse_m2, (ntiles + 127) / 128, 128, 0, d_tiles, d_imgs, din, d_dt, ntiles, d_err);
         if (lat) {
             // value streams on the side streams (joined before the residual kernels); LAT_M2_ORDER: 0..2 alphabets of at
             // most 16 symbols (direct table, 64 KiB), 3..7 larger alphabets (two-level), 8..16 contexts, 17 grey plane
@@ -1025,12 +1081,12 @@ static int decode_issue(xpngb_ctx* ctx, bool lat, xpngb_image* imgs, uint32_t n,
             auto k_dec_rans_v1_lat_grey = k_dec_rans_v1_lat; auto k_dec_rans_v1_lat_ctx = k_dec_rans_v1_lat;   // names for the profile report
             auto k_dec_rans_v1_lat_ctx_short = k_dec_rans_v1_lat;
             FORK_SIDE(0); side_busy[0] = true;
-            LAUNCH(k_dec_rans_v1_lat_values16, 3 * ntiles, 32, lat_smem(lut16), la);
+            LAUNCH_HI(k_dec_rans_v1_lat_values16, 3 * ntiles, 32, lat_smem(lut16), la);
             FORK_SIDE(1); side_busy[1] = true;
             la.j0 = 3; la.nj = 5; la.lut_bytes = LUT_TWO_14;
-            LAUNCH(k_dec_rans_v1_lat_values256, 5 * ntiles, 32, lat_smem(LUT_TWO_14), la);
+            LAUNCH_HI(k_dec_rans_v1_lat_values256, 5 * ntiles, 32, lat_smem(LUT_TWO_14), la);
             la.j0 = 17; la.nj = 1; la.lut_bytes = LUT_TWO_15;
-            LAUNCH(k_dec_rans_v1_lat_grey, ntiles, 32, lat_smem(LUT_TWO_15), la);
+            LAUNCH_HI(k_dec_rans_v1_lat_grey, ntiles, 32, lat_smem(LUT_TWO_15), la);
             BACK_TO_MAIN();
             // context streams: the few long ones (they bound the walk's start on real images) get the 64 KiB direct table,
             // the many short ones a two-level table on a side stream, so that everything stays resident
@@ -1038,12 +1094,12 @@ static int decode_issue(xpngb_ctx* ctx, bool lat, xpngb_image* imgs, uint32_t n,
             la.j0 = 8; la.nj = 9; la.lut_bytes = LUT_TWO_14; la.n_lo = 0; la.n_hi = direct ? CTX_LONG : ~0u;
             if (direct) {
                 FORK_SIDE(4); side_busy[4] = true;
-                LAUNCH(k_dec_rans_v1_lat_ctx_short, 9 * ntiles, 32, lat_smem(LUT_TWO_14), la);
+                LAUNCH_HI(k_dec_rans_v1_lat_ctx_short, 9 * ntiles, 32, lat_smem(LUT_TWO_14), la);
                 BACK_TO_MAIN();
                 la.lut_bytes = LUT_ONE_14; la.n_lo = CTX_LONG; la.n_hi = ~0u;
-                LAUNCH(k_dec_rans_v1_lat_ctx, 9 * ntiles, 32, lat_smem(LUT_ONE_14), la);
+                LAUNCH_HI(k_dec_rans_v1_lat_ctx, 9 * ntiles, 32, lat_smem(LUT_ONE_14), la);
                 JOIN_SIDE(4); side_busy[4] = false;       // the walk needs every context stream
-            } else LAUNCH(k_dec_rans_v1_lat_ctx, 9 * ntiles, 32, lat_smem(LUT_TWO_14), la);
+            } else LAUNCH_HI(k_dec_rans_v1_lat_ctx, 9 * ntiles, 32, lat_smem(LUT_TWO_14), la);
         } else {
             // the value streams (16-symbol alphabet: the longest chains of a tile; large alphabets) start first on the side
             // streams; contexts and the 8-symbol value streams on the main stream, followed by the walk
@@ -1052,12 +1108,12 @@ static int decode_issue(xpngb_ctx* ctx, bool lat, xpngb_image* imgs, uint32_t n,
             PdFillArgs fa{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, (uint8_t*)ctx->alpha.p, ntiles, 2 };
             auto k_dec_rans_pair_v1_s16 = k_dec_rans_pair<1, 15>; auto k_dec_rans_pair_v1_big = k_dec_rans_pair<1, 0>; auto k_dec_rans_pair_v1_s8 = k_dec_rans_pair<1, 8>;
             FORK_SIDE(0); side_busy[0] = true;
-            LAUNCH(k_dec_rans_pair_v1_s16, pd_grid(1), PD_WARPS * 32, 0, pd_args(W, PD_S16));
+            LAUNCH_HI(k_dec_rans_pair_v1_s16, pd_grid(1), PD_WARPS * 32, 0, pd_args(W, PD_S16));
             FORK_SIDE(1); side_busy[1] = true;
-            LAUNCH(k_dec_rans_pair_v1_big, pd_grid(5), PD_WARPS * 32, PD_WARPS * PD_BIG_BYTES, pd_args(W, PD_BIG));
+            LAUNCH_HI(k_dec_rans_pair_v1_big, pd_grid(5), PD_WARPS * 32, PD_WARPS * PD_BIG_BYTES, pd_args(W, PD_BIG));
             BACK_TO_MAIN();
-            LAUNCH(k_pd_fill_blocks, (17u * ntiles + 3) / 4, 128, 0, fa);   // run / raw blocks (contexts among them: before the walk)
-            LAUNCH(k_dec_rans_pair_v1_s8, pd_grid(11), PD_WARPS * 32, 0, pd_args(W, PD_S8));
+            LAUNCH_HI(k_pd_fill_blocks, (17u * ntiles + 3) / 4, 128, 0, fa);   // run / raw blocks (contexts among them: before the walk)
+            LAUNCH_HI(k_dec_rans_pair_v1_s8, pd_grid(11), PD_WARPS * 32, 0, pd_args(W, PD_S8));
         }
         if (launch_walk(2)) return 1;
     }
@@ -1066,7 +1122,7 @@ static int decode_issue(xpngb_ctx* ctx, bool lat, xpngb_image* imgs, uint32_t n,
         ChunkArgs ch{ d_tiles, d_seg_tile, d_imgs, d_dt, (const uint8_t*)ctx->nlseq.p, (const uint8_t*)ctx->streams.p, din,
                       (uint32_t*)ctx->ccnt.p, (uint32_t*)ctx->cbit.p, (uint32_t*)ctx->resv.p, ntiles, d_err };
         LAUNCH(k_dec_chunk_hist, nseg, 256, 0, ch);
-        LAUNCH(k_dec_chunk_scan, (ntiles + 3) / 4, 128, 0, ch);
+        LAUNCH_HI(k_dec_chunk_scan, (ntiles + 3) / 4, 128, 0, ch);
         for (int k = 0; k < xpngb_ctx::NSIDE; k++) if (k != 2 && side_busy[k]) JOIN_SIDE(k);
         if (any1) LAUNCH(k_dec_residuals<1>, nseg, 256, 0, ch);
         if (any2) { LAUNCH(k_dec_residuals<2>, nseg, 256, 0, ch); LAUNCH(k_dec_residuals_grey, nseg, 256, 0, ch); }

@@ -219,6 +219,7 @@ struct RansV2Args {
     uint8_t* blocks;          // block scratch (block_slice)
     uint32_t ntiles;
     uint32_t c0, nc;          // stream index range handled by this launch [c0, c0+nc)
+    const uint32_t* order = nullptr; const uint32_t* total = nullptr;   // pair encoders: sorted work list instead of the id range
 };
 
 template <int NSYM, int LANES>

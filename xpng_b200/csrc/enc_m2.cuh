@@ -110,6 +110,7 @@ struct RansV1Args {
     uint32_t c0, nc;
     uint32_t grey;             // 1: grey candidates, 0: RGB streams
     uint32_t nmin;             // skip alphabets of <= nmin symbols (done by the launch with the smaller table)
+    const uint32_t* order = nullptr; const uint32_t* total = nullptr;   // pair encoders: sorted work list instead of the id range
 };
 
 __device__ __constant__ const uint16_t M2_NSYM[17] = { 9, 9, 9, 9, 9, 9, 9, 9, 9, 8, 64, 8, 16, 32, 64, 128, 256 };

@@ -113,8 +113,17 @@ __global__ void __launch_bounds__(32) k_rans_v2_pair(RansV2Args A) {
     const uint32_t lane = threadIdx.x, h = lane & 1, blk = lane >> 1;
     if (h == 0) pair_put_ident(etab, etb, NSYM, blk);
     const uint32_t id = blockIdx.x * PAIR_BLK + blk;
-    const bool exists = id < A.nc * A.ntiles;
-    const uint32_t c = A.c0 + (exists ? id / A.ntiles : 0), tile = exists ? id % A.ntiles : 0;
+    bool exists; uint32_t c, tile;
+    if (A.order) {                                             // sorted work list (enc_order.cuh): longest blocks first
+        const uint32_t total = *A.total;
+        if (id - blk >= total) return;                         // warp-uniform
+        exists = id < total;
+        const uint32_t entry = exists ? A.order[id] : 0u;
+        tile = entry & 0xFFFFFFu; c = exists ? entry >> 24 : A.c0;
+    } else {
+        exists = id < A.nc * A.ntiles;
+        c = A.c0 + (exists ? id / A.ntiles : 0); tile = exists ? id % A.ntiles : 0;
+    }
     const TileDesc t = A.tiles[tile];
     TileState* st = A.state + tile;
     const uint32_t n = st->len[c];
@@ -185,8 +194,17 @@ __global__ void __launch_bounds__(32) k_rans_v1_pair(RansV1Args A) {
     const uint32_t lane = threadIdx.x, h = lane & 1, blk = lane >> 1;
     if (h == 0) pair_put_ident(etab, etb, NSYM, blk);
     const uint32_t id = blockIdx.x * PAIR_BLK + blk;
-    bool exists = id < A.nc * A.ntiles;
-    const uint32_t c = A.c0 + (exists ? id / A.ntiles : 0), tile = exists ? id % A.ntiles : 0;
+    bool exists; uint32_t c, tile;
+    if (A.order) {                                             // sorted work list (enc_order.cuh): longest blocks first
+        const uint32_t total = *A.total;
+        if (id - blk >= total) return;                         // warp-uniform
+        exists = id < total;
+        const uint32_t entry = exists ? A.order[id] : 0u;
+        tile = entry & 0xFFFFFFu; c = exists ? entry >> 24 : A.c0;
+    } else {
+        exists = id < A.nc * A.ntiles;
+        c = A.c0 + (exists ? id / A.ntiles : 0); tile = exists ? id % A.ntiles : 0;
+    }
     const uint8_t cls = A.tclass[tile];
     if (cls != (A.grey ? TC_GREY : TC_RGB)) exists = false;
     const TileDesc t = A.tiles[tile];
