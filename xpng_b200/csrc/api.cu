@@ -985,7 +985,7 @@ static int decode_issue(xpngb_ctx* ctx, bool lat, xpngb_image* imgs, uint32_t n,
     if (any1 || any2) {
         ENSURE(streams, P.str_total); ENSURE(nlseq, P.px_total); ENSURE(rows, P.row_total * sizeof(RowInfo));
         ENSURE(rowcnt, P.row_total * 4); ENSURE(edge, P.row_total * 16);
-        ENSURE(ccnt, (size_t)nseg * 9 * 4); ENSURE(cbit, (size_t)nseg * 4); ENSURE(resv, P.px_total * 4);
+        ENSURE(ccnt, (size_t)nseg * 9 * 4); ENSURE(cbit, (size_t)nseg * 4); ENSURE(resv, (P.px_total + 4 * P.row_total) * 4);
         if (P.any_rgba) { ENSURE(alpha, P.px_total); ENSURE(plane, P.px_total); }
         if (!lat) { ENSURE(pdw, 2 * pdw_bytes(pd_cap)); CK(cudaMemsetAsync(ctx->pdw.p, 0, 2 * pdw_bytes(pd_cap), ctx->stream)); }
         LAUNCH_HI(k_dec_tile_offsets, (n + 127) / 128, 128, 0, d_imgs, din, d_dt, n, d_err);
@@ -1117,17 +1117,21 @@ static int decode_issue(xpngb_ctx* ctx, bool lat, xpngb_image* imgs, uint32_t n,
         }
         if (launch_walk(2)) return 1;
     }
+    // batches: RGB tiles with word-aligned rows get the row-pitched residual plane and k_dec_unpredict_rgb
+    const uint32_t pitched = (!lat && !ctx->root->unr_force) ? 1u : 0u;
+    bool all_pitched = true;
+    for (const TileDesc& t : P.tiles) all_pitched &= tile_pitched(t);
     if (any1 || any2) {
         if (side_busy[2]) JOIN_SIDE(2);                   // the other family's nl sequences
         ChunkArgs ch{ d_tiles, d_seg_tile, d_imgs, d_dt, (const uint8_t*)ctx->nlseq.p, (const uint8_t*)ctx->streams.p, din,
-                      (uint32_t*)ctx->ccnt.p, (uint32_t*)ctx->cbit.p, (uint32_t*)ctx->resv.p, ntiles, d_err };
+                      (uint32_t*)ctx->ccnt.p, (uint32_t*)ctx->cbit.p, (uint32_t*)ctx->resv.p, ntiles, d_err, pitched };
         LAUNCH(k_dec_chunk_hist, nseg, 256, 0, ch);
         LAUNCH_HI(k_dec_chunk_scan, (ntiles + 3) / 4, 128, 0, ch);
         for (int k = 0; k < xpngb_ctx::NSIDE; k++) if (k != 2 && side_busy[k]) JOIN_SIDE(k);
         if (any1) LAUNCH(k_dec_residuals<1>, nseg, 256, 0, ch);
         if (any2) { LAUNCH(k_dec_residuals<2>, nseg, 256, 0, ch); LAUNCH(k_dec_residuals_grey, nseg, 256, 0, ch); }
         UnpredArgs ua{ d_tiles, d_imgs, d_dt, din, (const uint32_t*)ctx->resv.p, (const uint8_t*)ctx->plane.p, (const RowInfo*)ctx->rows.p,
-                       (uint4*)ctx->edge.p, 0 };
+                       (uint4*)ctx->edge.p, 0, pitched };
         uint32_t maxw = 0;
         for (const TileDesc& t : P.tiles) if (t.w > maxw) maxw = t.w;
         // 16 warps per tile when the call has fewer tiles than SMs (shortest band pipeline), 8 up to a few per SM; beyond
@@ -1135,7 +1139,12 @@ static int decode_issue(xpngb_ctx* ctx, bool lat, xpngb_image* imgs, uint32_t n,
         // with thousands of tiles the tiles themselves are the parallelism
         uint32_t nw = call_tiles <= 148 ? 16u : (call_tiles <= ctx->root->unr_multi_max_tiles ? 8u : 1u);
         if (ctx->root->unr_force) nw = ctx->root->unr_force;
-        if (nw == 16) LAUNCH(k_dec_unpredict_rows<16>, ntiles, 16 * 32, 16 * 2 * 32 * UNR_PITCH, ua);
+        if (pitched) {   // batches: one warp per RGB tile on the row-pitched residual plane; whatever it cannot take goes on below
+            LAUNCH(k_dec_unpredict_rgb, ntiles, 32, 0, ua);
+            if (all_pitched) nw = 0;
+        }
+        if (nw == 0) { }
+        else if (nw == 16) LAUNCH(k_dec_unpredict_rows<16>, ntiles, 16 * 32, 16 * 2 * 32 * UNR_PITCH, ua);
         else if (nw == 8) LAUNCH(k_dec_unpredict_rows<8>, ntiles, 8 * 32, 8 * 2 * 32 * UNR_PITCH, ua);
         else if (nw == 4) LAUNCH(k_dec_unpredict_rows<4>, ntiles, 4 * 32, 4 * 2 * 32 * UNR_PITCH, ua);
         else if (nw == 2) LAUNCH(k_dec_unpredict_rows<2>, ntiles, 2 * 32, 2 * 2 * 32 * UNR_PITCH, ua);

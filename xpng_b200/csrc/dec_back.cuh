@@ -226,10 +226,20 @@ struct ChunkArgs {
     const uint8_t* in;
     uint32_t* ccnt;      // [nseg][9] counts, then (after the scan) exclusive prefixes per nl
     uint32_t* cbit;      // [nseg] bit offset of the chunk's first residual (level 1)
-    uint32_t* resv;      // residual plane per tile at px_off: u0 | u1 << 8 | u2 << 16 per coded pixel
+    uint32_t* resv;      // residual plane per tile (resv_base): u0 | u1 << 8 | u2 << 16 per coded pixel
     uint32_t ntiles;
     int* err;
+    uint32_t pitched;    // 1: RGB tiles that k_dec_unpredict_rgb takes get the row-pitched layout (tile_pitched)
 };
+
+// Residual plane of a tile.  Linear layout: entry k = k-th coded pixel (raster index k + 1 for RGB).  Row-pitched layout
+// (batches, RGB tiles with word-aligned rows): pixel (x, y) at y * pitch + x, pitch = w rounded up to 4 words, so that a
+// row starts 16-byte aligned and k_dec_unpredict_rgb fetches four residuals per load.  The base leaves 4 words per row
+// of every earlier tile for the padding (px_off and row_off are running sums over the chunk's tiles).
+__device__ __forceinline__ uint64_t resv_base(const TileDesc& t) { return t.px_off + 4ull * t.row_off; }
+__host__ __device__ __forceinline__ bool tile_pitched(const TileDesc& t) {
+    return t.pxsz == 3 && t.w <= 672u && ((t.src_off | t.bpr) & 3u) == 0;   // 672 = UNR_MAXW
+}
 
 __device__ __forceinline__ bool coded_tile(const DecTile* d) { return d->m != 0 && d->m < 0x20; }   // RGB entropy-coded tile
 
@@ -305,9 +315,14 @@ __global__ void __launch_bounds__(256) k_dec_residuals(ChunkArgs A) {
     if (c0 >= d->nsym) return;
     const uint32_t c1 = min(c0 + (uint32_t)SEG, d->nsym);
     const uint8_t* seq = A.nlseq + t.px_off;
-    uint32_t* res = A.resv + t.px_off;
+    uint32_t* res = A.resv + resv_base(t);
     const uint8_t* blob = A.in + d->blob_off;
     const uint32_t e0 = c0 + tid * 16;
+    // destination index of entry e0 and what to add at a row end (0: linear layout)
+    const bool pitched = A.pitched && tile_pitched(t);
+    uint32_t rx = 0, ri = e0, rskip = 0;
+    if (pitched) { const uint32_t ry = (e0 + 1) / t.w; rx = (e0 + 1) - ry * t.w; rskip = ((t.w + 3u) & ~3u) - t.w; ri = ry * (t.w + rskip) + rx; }
+    auto put = [&](uint32_t v) { res[ri] = v; ri++; if (pitched && ++rx == t.w) { rx = 0; ri += rskip; } };
     uint32_t w[4] = { 0, 0, 0, 0 };
     if (e0 < c1) { const uint4 q = *reinterpret_cast<const uint4*>(seq + e0); w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w; }
     if (MODE == 1) {
@@ -335,7 +350,7 @@ __global__ void __launch_bounds__(256) k_dec_residuals(ChunkArgs A) {
                 v = (f >> (2 * nl)) | (((f >> nl) & mk) << 8) | ((f & mk) << 16);
                 bit += 3 * nl;
             }
-            res[e0 + e] = v;
+            put(v);
         }
     } else {
         Cnt9 cc{ 0, 0, 0 };
@@ -360,7 +375,7 @@ __global__ void __launch_bounds__(256) k_dec_residuals(ChunkArgs A) {
                 else if (nl == 2) { const uint32_t b = sbase[so + rank]; v = (b >> 4) | (((b >> 2) & 3u) << 8) | ((b & 3u) << 16); }
                 else { const uint8_t* q = sbase + so + 3ull * rank; v = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16); }
             }
-            res[e0 + e] = v;
+            put(v);
         }
     }
 }
@@ -373,7 +388,11 @@ __global__ void __launch_bounds__(256) k_dec_residuals_grey(ChunkArgs A) {
     if (A.imgs[t.img].mode != 2 || (d->m >> 4) != 2 || (d->m & 8) || d->m == 0xFE || d->m == 0xFF) return;
     const uint32_t c0 = (gseg - t.seg0) * SEG, c1 = min(c0 + (uint32_t)SEG, t.npx - 1);
     const uint8_t* s = A.streams + t.str_off + d->blk[0].soff;
-    uint32_t* res = A.resv + t.px_off;
+    uint32_t* res = A.resv + resv_base(t);
+    if (A.pitched && tile_pitched(t)) {
+        const uint32_t pitch = (t.w + 3u) & ~3u;
+        for (uint32_t k = c0 + threadIdx.x; k < c1; k += 256) { const uint32_t y = (k + 1) / t.w, x = (k + 1) - y * t.w; res[y * pitch + x] = (uint32_t)s[k] * 0x010101u; }
+    } else
     for (uint32_t k = c0 + threadIdx.x; k < c1; k += 256) res[k] = (uint32_t)s[k] * 0x010101u;
 }
 
@@ -414,13 +433,14 @@ struct UnpredArgs {
     const RowInfo* rows;      // RGBA: first residual index of each row
     uint4* edge;              // strip hand-over scratch per tile row (tiles wider than UNP_THREADS)
     uint32_t min_w;           // k_dec_unpredict only: skip tiles up to this width (they go to k_dec_unpredict_rows)
+    uint32_t pitched;         // 1: tiles with tile_pitched() belong to k_dec_unpredict_rgb (row-pitched residual plane)
 };
 
 template <int PXSZ>
 __device__ __forceinline__ void unpredict_tile(const UnpredArgs& A, const TileDesc& t, const DecTile* d, uint2 (*slots)[UNP_THREADS + 1]) {
     const uint32_t tid = threadIdx.x;
     const uint8_t* blob = A.in + d->blob_off;
-    const uint32_t* res = A.resv + t.px_off;
+    const uint32_t* res = A.resv + resv_base(t);
     const uint8_t* pl = A.plane + t.px_off;
     const RowInfo* rows = A.rows + t.row_off;
     uint8_t* dst = reinterpret_cast<uint8_t*>(t.src_off);
@@ -494,7 +514,7 @@ __global__ void __launch_bounds__(UNP_THREADS) k_dec_unpredict(UnpredArgs A) {
     if (mode == 7 || (mode & 0x100)) return;
     const DecTile* d = A.dt + tile;
     if (d->m == 0 || d->m == 0xFE || d->m == 0xFF || ((d->m >> 4) == 2 && (d->m & 8))) return;
-    if (t.w <= A.min_w) return;
+    if (t.w <= A.min_w) return;   // (wider than UNR_MAXW: never a pitched tile)
     if (t.pxsz == 4) unpredict_tile<4>(A, t, d, slots);
     else unpredict_tile<3>(A, t, d, slots);
 }
@@ -561,7 +581,7 @@ __device__ __forceinline__ void unpredict_rows(const UnpredArgs& A, const TileDe
                                                volatile uint32_t* prog, uint8_t* stage) {
     const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint8_t* blob = A.in + d->blob_off;
-    const uint32_t* res = A.resv + t.px_off;
+    const uint32_t* res = A.resv + resv_base(t);
     const uint8_t* pl = A.plane + t.px_off;
     const RowInfo* rows = A.rows + t.row_off;
     uint8_t* dst = reinterpret_cast<uint8_t*>(t.src_off);
@@ -693,6 +713,7 @@ __global__ void __launch_bounds__(NW * 32) k_dec_unpredict_rows(UnpredArgs A) {
     const DecTile* d = A.dt + tile;
     if (d->m == 0 || d->m == 0xFE || d->m == 0xFF || ((d->m >> 4) == 2 && (d->m & 8))) return;
     if (t.w > UNR_MAXW) return;                       // very wide, flat tiles (thin images): k_dec_unpredict
+    if (A.pitched && tile_pitched(t)) return;         // k_dec_unpredict_rgb
     if (threadIdx.x < NW) prog_s[threadIdx.x] = 0;
     __syncthreads();
     // specialise the inner loop on the tile's predictor (grey tiles: m & 3; colour tiles: avg2 / grad3, optional G)
@@ -706,6 +727,120 @@ __global__ void __launch_bounds__(NW * 32) k_dec_unpredict_rows(UnpredArgs A) {
     else if (pm == 2) { if (G) unpredict_rows<3, 2, true, NW>(A, t, d, brow, prog_s, unr_stage); else unpredict_rows<3, 2, false, NW>(A, t, d, brow, prog_s, unr_stage); }
     else if (pm == 1) unpredict_rows<3, 1, false, NW>(A, t, d, brow, prog_s, unr_stage);
     else unpredict_rows<3, 0, false, NW>(A, t, d, brow, prog_s, unr_stage);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Un-predict for batches: one warp per RGB tile, the row-band wavefront of unpredict_rows with the memory side rebuilt
+// for thousands of resident warps (ncu on 4000 tiles: the older kernel issued one instruction per 25 cycles and warp,
+// 58 % of it waiting for shared memory, L1 hit rate 24 % on its word-sized residual loads, 19 warps per SM for its
+// 8.4 KB stage):
+//   * residuals come from the row-pitched plane, FOUR per 128-bit load, twelve steps ahead, into a 16-slot register ring;
+//   * finished pixels are packed in a 96-bit shift register and leave as three aligned words per four pixels, straight
+//     to global memory (each lane writes its own row; L2 merges the sectors): no staging buffer, no flush loop;
+//   * shared memory per warp is the 2.7 KB boundary row only, so registers (64) bound the residency at 32 warps per SM.
+// Requires word-aligned rows (tile_pitched).  libxpng.c:811-814, :866-897, :911-914.
+// ------------------------------------------------------------------------------------------------
+template <int PM, bool GSUB>
+__device__ __forceinline__ void unpredict_rgb(const UnpredArgs& A, const TileDesc& t, const DecTile* d, uint32_t* brow) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint8_t* blob = A.in + d->blob_off;
+    const uint32_t w = t.w, pitch = (w + 3u) & ~3u;
+    const uint32_t* res = A.resv + resv_base(t);
+    uint8_t* dst = reinterpret_cast<uint8_t*>(t.src_off);
+    const uint32_t fp = ld32u(blob + 8);   // first pixel, MSB-first bits
+    const uint32_t first = (d->m >> 4) == 2 ? (fp >> 24) * 0x010101u : (((fp >> 24) & 255u) | (((fp >> 16) & 255u) << 8) | (((fp >> 8) & 255u) << 16));
+    const uint32_t nbands = (t.h + 31) / 32;
+    constexpr int RING = 16, AHEAD = 12;
+    for (uint32_t b = 0; b < nbands; b++) {
+        const uint32_t y = b * 32 + lane;
+        const bool rowok = y < t.h, row0 = y == 0;
+        const uint32_t lastlane = min(31u, t.h - 1 - b * 32);
+        const uint32_t* rrow = res + (uint64_t)y * pitch;            // 16-byte aligned
+        uint8_t* orow = dst + (uint64_t)y * t.bpr;                    // word aligned
+        uint32_t left = 0, uprev = 0, prevout = 0, a0 = 0, a1 = 0, a2 = 0;
+        uint32_t rn[RING];
+#pragma unroll
+        for (int k = 0; k < RING; k++) rn[k] = 0;
+        if (rowok) {   // columns 0 .. 11: column c is consumed at step c + lane, i.e. from slot (c + lane) % RING
+#pragma unroll
+            for (int g = 0; g < AHEAD / 4; g++) {
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (4u * g < pitch) v = __ldg(reinterpret_cast<const uint4*>(rrow) + g);
+                const uint32_t vv[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const uint32_t slot = (lane + 4u * g + q) % RING;
+#pragma unroll
+                    for (int k = 0; k < RING; k++) rn[k] = slot == (uint32_t)k ? vv[q] : rn[k];
+                }
+            }
+        }
+        const uint32_t steps = (w + 31 + RING - 1) / RING * RING;
+        for (uint32_t s0 = 0; s0 < steps; s0 += RING) {
+#pragma unroll
+            for (int j = 0; j < RING; j++) {
+                const uint32_t s = s0 + j;
+                const uint32_t x = s - lane;                          // lanes that have not started yet wrap around: x >= w
+                const bool act = rowok && x < w;
+                const uint32_t ub = brow[min(s, w - 1)];              // row above the band (band 0 never uses it)
+                uint32_t U = __shfl_up_sync(0xffffffffu, prevout, 1);
+                U = lane == 0 ? ub : U;
+                const uint32_t rv = rn[j];
+                {   // refill: at x = 0 (mod 4) the four residuals of columns x + 12 .. x + 15 go to the slots consumed last
+                    const uint32_t go = (act && (x & 3u) == 0 && x + AHEAD < pitch) ? 1u : 0u;
+                    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %5, 0;\n @q ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n}"
+                                 : "+r"(rn[(j + 12) % RING]), "+r"(rn[(j + 13) % RING]), "+r"(rn[(j + 14) % RING]), "+r"(rn[(j + 15) % RING])
+                                 : "l"(rrow + x + AHEAD), "r"(go));
+                }
+                uint32_t pix = 0;
+                if (act) {
+                    uint32_t r = swar_unzz(rv);
+                    if (GSUB) { const uint32_t rg = swar_add(r, ((r >> 8) & 0xFFu) * 0x00010001u); r = (x && !row0) ? rg : r; }
+                    uint32_t pd = PM == 0 ? left : (PM == 1 ? U : (PM == 2 ? swar_avg2(left, U) : swar_grad3(left, U, uprev)));
+                    pd = row0 ? left : (x == 0 ? U : pd);
+                    const uint32_t val = swar_add(r, pd) & 0x00FFFFFFu;
+                    pix = (x | y) == 0 ? first : val;
+                    left = pix;
+                    // 96-bit shift register: after pixels 4k .. 4k + 3 it holds their twelve bytes in memory order
+                    a0 = __funnelshift_r(a0, a1, 24); a1 = __funnelshift_r(a1, a2, 24); a2 = __funnelshift_r(a2, pix, 24);
+                    if (lane == lastlane) brow[x] = pix;
+                    if ((x & 3u) == 3u) {
+                        uint32_t* o = reinterpret_cast<uint32_t*>(orow + 3u * (x - 3u));
+                        o[0] = a0; o[1] = a1; o[2] = a2;
+                    } else if (x == w - 1) {                         // 1 .. 3 pixels left over at the row end: byte stores
+                        const uint32_t np = (x & 3u) + 1u, sh = 24u * (4u - np);   // bring them down to bit 0 (sh = 24, 48, 72)
+                        uint32_t t0 = a0, t1 = a1, t2 = a2;
+                        if (sh >= 64) { t0 = t2; t1 = 0; t2 = 0; } else if (sh >= 32) { t0 = t1; t1 = t2; t2 = 0; }
+                        const uint32_t rs = sh & 31u;
+                        const uint32_t b0 = __funnelshift_r(t0, t1, rs), b1 = __funnelshift_r(t1, t2, rs), b2 = t2 >> rs;
+                        uint8_t* o = orow + 3u * (x + 1u - np);
+                        for (uint32_t k = 0; k < 3u * np; k++) { const uint32_t wv = k < 4u ? b0 : (k < 8u ? b1 : b2); o[k] = (uint8_t)(wv >> (8u * (k & 3u))); }
+                    }
+                }
+                uprev = U;
+                prevout = pix;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(32) k_dec_unpredict_rgb(UnpredArgs A) {
+    __shared__ uint32_t brow[UNR_MAXW];
+    const uint32_t tile = blockIdx.x;
+    const TileDesc t = A.tiles[tile];
+    const uint32_t mode = A.imgs[t.img].mode;
+    if (mode == 7 || (mode & 0x100)) return;
+    const DecTile* d = A.dt + tile;
+    if (d->m == 0 || d->m == 0xFE || d->m == 0xFF || ((d->m >> 4) == 2 && (d->m & 8))) return;
+    if (!tile_pitched(t)) return;                      // RGBA, very wide or unaligned tiles: the older kernels
+    const bool grey = (d->m >> 4) == 2;
+    const uint32_t pm = grey ? (d->m & 3u) : (((d->m >> 1) & 1u) ? 3u : 2u);
+    const bool G = !grey && (d->m & 1u);
+    if (pm == 3) { if (G) unpredict_rgb<3, true>(A, t, d, brow); else unpredict_rgb<3, false>(A, t, d, brow); }
+    else if (pm == 2) { if (G) unpredict_rgb<2, true>(A, t, d, brow); else unpredict_rgb<2, false>(A, t, d, brow); }
+    else if (pm == 1) unpredict_rgb<1, false>(A, t, d, brow);
+    else unpredict_rgb<0, false>(A, t, d, brow);
 }
 
 // Raw grey plane (level 2, m = 0x28, libxpng.c:875-879)
