@@ -61,24 +61,37 @@ __device__ __forceinline__ void f2_copy_row(uint8_t* pixb, uint32_t d, const uin
     const int32_t e0 = (int32_t)d - (int32_t)lead;             // destination of byte 0 of vector 0 (may be negative)
     const uint32_t b = (uint32_t)e0 & 3u, sh = 8u * b;
     uint32_t carry = 0;                                         // last word of the vector before this round's first
-    for (uint32_t v0 = 0; v0 < nvec + 1; v0 += 32) {
-        const uint32_t v = v0 + lane;
-        uint4 V = make_uint4(0, 0, 0, 0);
-        if (v < nvec) V = f2_ld16(a0 + 16ull * v, limit);
-        uint32_t prev = __shfl_up_sync(0xffffffffu, V.w, 1);
-        if (lane == 0) prev = carry;
-        carry = __shfl_sync(0xffffffffu, V.w, 31);
-        if (v <= nvec) {
-            const uint32_t o[4] = { b ? __funnelshift_l(prev, V.x, sh) : V.x, b ? __funnelshift_l(V.x, V.y, sh) : V.y,
-                                    b ? __funnelshift_l(V.y, V.z, sh) : V.z, b ? __funnelshift_l(V.z, V.w, sh) : V.w };
-            const int32_t wb = e0 - (int32_t)b + 16 * (int32_t)v;   // byte offset of the first destination word of this vector
+    // rounds of 32 vectors, four rounds per batch: all loads of a batch are issued before the first is used (a row of a
+    // 444-pixel tile is three rounds: one exposed memory latency per row instead of three)
+    for (uint32_t vb = 0; vb < nvec + 1; vb += 128) {
+        uint4 VV[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int32_t p = wb + 4 * i;
-                if (p >= (int32_t)d && p + 4 <= (int32_t)(d + nb)) *reinterpret_cast<uint32_t*>(pixb + p) = o[i];
-                else if (p + 4 > (int32_t)d && p < (int32_t)(d + nb)) {
+        for (int r = 0; r < 4; r++) {
+            const uint32_t v = vb + 32u * r + lane;
+            VV[r] = make_uint4(0, 0, 0, 0);
+            if (v < nvec) VV[r] = f2_ld16(a0 + 16ull * v, limit);
+        }
 #pragma unroll
-                    for (int k = 0; k < 4; k++) if (p + k >= (int32_t)d && p + k < (int32_t)(d + nb)) pixb[p + k] = (uint8_t)(o[i] >> (8 * k));
+        for (int r = 0; r < 4; r++) {
+            const uint32_t v0 = vb + 32u * r;
+            if (v0 >= nvec + 1) break;                          // warp-uniform
+            const uint32_t v = v0 + lane;
+            const uint4 V = VV[r];
+            uint32_t prev = __shfl_up_sync(0xffffffffu, V.w, 1);
+            if (lane == 0) prev = carry;
+            carry = __shfl_sync(0xffffffffu, V.w, 31);
+            if (v <= nvec) {
+                const uint32_t o[4] = { b ? __funnelshift_l(prev, V.x, sh) : V.x, b ? __funnelshift_l(V.x, V.y, sh) : V.y,
+                                        b ? __funnelshift_l(V.y, V.z, sh) : V.z, b ? __funnelshift_l(V.z, V.w, sh) : V.w };
+                const int32_t wb = e0 - (int32_t)b + 16 * (int32_t)v;   // byte offset of the first destination word of this vector
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int32_t p = wb + 4 * i;
+                    if (p >= (int32_t)d && p + 4 <= (int32_t)(d + nb)) *reinterpret_cast<uint32_t*>(pixb + p) = o[i];
+                    else if (p + 4 > (int32_t)d && p < (int32_t)(d + nb)) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) if (p + k >= (int32_t)d && p + k < (int32_t)(d + nb)) pixb[p + k] = (uint8_t)(o[i] >> (8 * k));
+                    }
                 }
             }
         }
@@ -132,10 +145,18 @@ __device__ __forceinline__ void front2_segment(const FrontArgs& A, Front2Shared&
         }
         uint32_t Uw[13];                                        // the same 52 bytes one tile row up
         {
-            const uint32_t ub = B0 - 3 * w - 4, ush = (ub & 3u) * 8u, ui = ub >> 2;
+            // 14 words from word ui = (B0 - 3w - 4) >> 2: five aligned 128-bit loads (threads are 12 words apart: conflict-free,
+            // where word loads at that stride collide four ways); ui & 3 is the same for every thread of the CTA
+            const uint32_t ub = B0 - 3 * w - 4, ush = (ub & 3u) * 8u, ui = ub >> 2, ua = ui & 3u;
+            uint32_t v20[20];
+#pragma unroll
+            for (int q = 0; q < 5; q++) {
+                const uint4 v = *reinterpret_cast<const uint4*>(&S.pix[(ui & ~3u) + 4 * q]);
+                v20[4 * q] = v.x; v20[4 * q + 1] = v.y; v20[4 * q + 2] = v.z; v20[4 * q + 3] = v.w;
+            }
             uint32_t raw[14];
 #pragma unroll
-            for (int q = 0; q < 14; q++) raw[q] = S.pix[ui + q];
+            for (int q = 0; q < 14; q++) raw[q] = ua == 0 ? v20[q] : (ua == 1 ? v20[q + 1] : (ua == 2 ? v20[q + 2] : v20[q + 3]));
 #pragma unroll
             for (int q = 0; q < 13; q++) Uw[q] = __funnelshift_r(raw[q], raw[q + 1], ush);
         }
