@@ -251,20 +251,28 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     lib = xpng_b200.lib()
-    # one codec context per level: the two level jobs (encode -> gather -> decode) are independent and are issued from two
-    # host threads, so the serial-chain phases of one overlap the data-parallel phases of the other on the device
-    cds = {lv: xpng_b200.Codec(local_rank) for lv in LEVELS}
-    cd = cds[LEVELS[0]]
-    stream = torch.cuda.ExternalStream(cd.stream, device=dev)
+    # A step is a set of JOBS: (level, part of the shard) -> encode, [size/offset gather once the level is encoded], decode.
+    # Every job has its own codec context and host thread, so the serial-chain phases of one job overlap the
+    # data-parallel phases of the others on the device, and with host buffers the pixel uploads of one job's encode
+    # run next to the pixel downloads of another job's decode (both PCIe directions busy).
     F = args.frames
     lo, hi = shard.shard_range(F, rank, world)
     n = hi - lo
+    PARTS = max(1, min(args.parts, n if n else 1))
+    part_rng = [shard.shard_range(n, p, PARTS) for p in range(PARTS)]          # frame ranges of the parts inside the shard
+    JOBS = [(lv, p) for lv in LEVELS for p in range(PARTS)]
+    cds = {j: xpng_b200.Codec(local_rank) for j in JOBS}
+    cd = cds[JOBS[0]]
+    stream = torch.cuda.ExternalStream(cd.stream, device=dev)
     gtag = f"bench{os.environ.get('MASTER_PORT', '0')}_{os.environ.get('TORCHELASTIC_RUN_ID', os.getppid() if world > 1 else os.getpid())}"
     gathers = {lv: shard.Gather(f"{gtag}_L{lv}", rank, world, F) for lv in LEVELS}
     npx_frame = FW * FH
+    FRAME_B = npx_frame * 3                      # 6220800: a multiple of 16, frame k of the shard sits at k * FRAME_B
+    FILE_B = (8 + FRAME_B + 15) & ~15            # xpngb_encode_bound of one frame: part p's files start at a * FILE_B
     shapes = [(FH, FW, 3)] * n
     descs0, total = xpng_b200.Codec.layout(shapes)
     cap = int(lib.xpngb_encode_bound(descs0, n)) if n else 16
+    assert total == n * FRAME_B and (cap == n * FILE_B or not n)
     # ---- frames of this rank's shard, generated straight into pinned host memory, then uploaded
     h_px = torch.empty(max(total, 16) + 64, dtype=torch.uint8).pin_memory()
     frames_sample = {}
@@ -281,61 +289,82 @@ def run_ours(args, rank, world, local_rank):
     d_px = h_px.to(dev)
     d_files = {lv: torch.zeros(cap + 64, dtype=torch.uint8, device=dev) for lv in LEVELS}
     d_back = {lv: torch.zeros(max(total, 16) + 64, dtype=torch.uint8, device=dev) for lv in LEVELS}
-    state = {"launches": {lv: 0 for lv in LEVELS}, "calls": {}, "sizes": {}, "offs": {}, "sha": {}, "table_sha": None}
-    pool = ThreadPoolExecutor(len(LEVELS))
+    state = {"launches": 0, "calls": {}, "sizes": {lv: [0] * n for lv in LEVELS}, "offs": {lv: [0] * n for lv in LEVELS}, "sha": {}, "table_sha": None}
+    pool = ThreadPoolExecutor(len(JOBS))
+    lock = threading.Lock()
 
-    def new_descs(zero_dims=False):
-        d = xpng_b200.Codec.layout(shapes)[0]
+    def part_descs(m, zero_dims=False):
+        d = xpng_b200.Codec.layout(shapes[:m])[0]
         if zero_dims:
             for x in d:
                 x.w = x.h = 0
         return d
 
-    def level_job(lv, px, files, back, on_dev, rec):
-        c = cds[lv]
+    def job(i, px, files, back, on_dev, rec, chained, evs, left):
+        lv, p = JOBS[i]
+        c = cds[JOBS[i]]
+        a, b = part_rng[p]
+        m = b - a
+        if chained and i > 0:
+            evs[i - 1].wait()                        # my encode starts when the previous job has encoded
         t0 = time.perf_counter()
-        if n:
-            offs, sz = c.encode_raw(lv, new_descs(), n, px.data_ptr(), total, on_dev, files[lv].data_ptr(), files[lv].numel() - 64, on_dev)
-            state["launches"][lv] += c.last_launches
+        # the part's region of the level's file arena: device arenas hold the bound, the pinned host arenas what the parts need
+        fbase, fcap = (a * FILE_B, m * FILE_B) if on_dev else state["hregion"][lv][p]
+        if m:
+            offs, sz = c.encode_raw(lv, part_descs(m), m, px.data_ptr() + a * FRAME_B, m * FRAME_B, on_dev,
+                                    files[lv].data_ptr() + fbase, fcap, on_dev)
+            launches = c.last_launches
+            state["sizes"][lv][a:b] = [int(sz[k]) for k in range(m)]
+            state["offs"][lv][a:b] = [fbase + int(offs[k]) for k in range(m)]
         else:
-            offs, sz = (C.c_uint64 * 1)(), (C.c_uint64 * 1)()
+            offs, sz, launches = (C.c_uint64 * 1)(), (C.c_uint64 * 1)(), 0
         t1 = time.perf_counter()
-        g_offs, g_sizes = gathers[lv].sizes(F, [int(sz[i]) for i in range(n)])       # the one exchange between ranks
-        h = hashlib.sha256()
-        h.update(np.asarray(g_sizes, dtype=np.uint64).tobytes()); h.update(np.asarray(g_offs, dtype=np.uint64).tobytes())
-        state["sha"][lv] = h.hexdigest()
+        evs[i].set()
+        with lock:
+            left[lv] -= 1
+            last = left[lv] == 0
+        if last:                                     # the level is encoded: the one exchange between ranks
+            g_offs, g_sizes = gathers[lv].sizes(F, list(state["sizes"][lv]))
+            h = hashlib.sha256()
+            h.update(np.asarray(g_sizes, dtype=np.uint64).tobytes()); h.update(np.asarray(g_offs, dtype=np.uint64).tobytes())
+            state["sha"][lv] = h.hexdigest()
         t2 = time.perf_counter()
-        if n:
-            c.decode_raw(new_descs(True), n, files[lv].data_ptr(), files[lv].numel() - 64, on_dev, offs, sz, back[lv].data_ptr(), total, on_dev)
-            state["launches"][lv] += c.last_launches
+        if m:
+            c.decode_raw(part_descs(m, True), m, files[lv].data_ptr() + fbase, fcap, on_dev, offs, sz,
+                         back[lv].data_ptr() + a * FRAME_B, m * FRAME_B, on_dev)
+            launches += c.last_launches
         t3 = time.perf_counter()
-        state["sizes"][lv] = [int(sz[i]) for i in range(n)]; state["offs"][lv] = [int(offs[i]) for i in range(n)]
-        if rec:
-            cc = state["calls"]
-            cc[f"enc{lv}"] = cc.get(f"enc{lv}", 0.0) + (t1 - t0); cc[f"gather{lv}"] = cc.get(f"gather{lv}", 0.0) + (t2 - t1)
-            cc[f"dec{lv}"] = cc.get(f"dec{lv}", 0.0) + (t3 - t2)
+        with lock:
+            state["launches"] += launches
+            if rec:
+                cc = state["calls"]
+                cc[f"enc{lv}"] = cc.get(f"enc{lv}", 0.0) + (t1 - t0); cc[f"dec{lv}"] = cc.get(f"dec{lv}", 0.0) + (t3 - t2)
+                if last:
+                    cc[f"gather{lv}"] = cc.get(f"gather{lv}", 0.0) + (t2 - t1)
 
-    def step(px, files, back, on_dev, rec, concurrent=True):
-        if concurrent:
-            for fu in [pool.submit(level_job, lv, px, files, back, on_dev, rec) for lv in LEVELS]:
-                fu.result()
+    def step(px, files, back, on_dev, rec, schedule="concurrent"):
+        evs = [threading.Event() for _ in JOBS]
+        left = {lv: PARTS for lv in LEVELS}
+        if schedule == "sequential":
+            for i in range(len(JOBS)):
+                job(i, px, files, back, on_dev, rec, False, evs, left)
         else:
-            for lv in LEVELS:
-                level_job(lv, px, files, back, on_dev, rec)
+            for fu in [pool.submit(job, i, px, files, back, on_dev, rec, schedule == "chained", evs, left) for i in range(len(JOBS))]:
+                fu.result()
         state["table_sha"] = hashlib.sha256("".join(state["sha"][lv] for lv in LEVELS).encode()).hexdigest()[:16]
 
-    def timed(px, files, back, on_dev, steps, warmup, concurrent=True):
+    def timed(px, files, back, on_dev, steps, warmup, schedule="concurrent"):
         for _ in range(warmup):
-            step(px, files, back, on_dev, False, concurrent)
+            step(px, files, back, on_dev, False, schedule)
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
-        state["launches"] = {lv: 0 for lv in LEVELS}; state["calls"] = {}
+        state["launches"] = 0; state["calls"] = {}
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record(stream)
         for _ in range(steps):
-            step(px, files, back, on_dev, True, concurrent)   # every call returns with its device work done: e1 closes the region
+            step(px, files, back, on_dev, True, schedule)   # every call returns with its device work done: e1 closes the region
         e1.record(stream)
         e1.synchronize()
         torch.cuda.synchronize()
@@ -360,23 +389,30 @@ def run_ours(args, rank, world, local_rank):
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_dev, calls_conc = timed(d_px, d_files, d_back, 1, args.steps, args.warmup)
-    n_launch = sum(state["launches"].values())
+    ms_dev, calls_conc = timed(d_px, d_files, d_back, 1, args.steps, args.warmup, args.schedule)
+    n_launch = state["launches"]
     clocks = sampler.stop()
     for lv in LEVELS:
         if n:
             assert torch.equal(d_back[lv][:total], d_px[:total]), f"rank {rank} level {lv}: decoded pixels differ after the timed steps"
     # the same step with the two level jobs one after the other: per-call device-resident times for the breakdown
-    ms_seq, calls_dev = timed(d_px, d_files, d_back, 1, 2, 1, concurrent=False)
+    ms_seq, calls_dev = timed(d_px, d_files, d_back, 1, 2, 1, "sequential")
     table_sha = state["table_sha"]
     dev_offs = {lv: list(state["offs"][lv]) for lv in LEVELS}     # the device arena's layout (the host leg packs differently)
     dev_sizes = {lv: list(state["sizes"][lv]) for lv in LEVELS}
     # ---- end to end: pinned host buffers through the same C ABI calls
-    hcap = int(max(xpng_bytes.values()) * 1.05) + (1 << 20) if n else 16
-    h_files = {lv: torch.empty(hcap + 64, dtype=torch.uint8).pin_memory() for lv in LEVELS}
+    state["hregion"] = {}
+    h_files = {}
+    for lv in LEVELS:      # host arenas: one region per part, sized from the sizes the device leg produced (+5 %)
+        regs, base = [], 0
+        for (a, b) in part_rng:
+            need = (int(sum(dev_sizes[lv][a:b]) * 1.05) + (1 << 20) + 15) & ~15
+            regs.append((base, need)); base += need
+        state["hregion"][lv] = regs
+        h_files[lv] = torch.empty(max(base, 16) + 64, dtype=torch.uint8).pin_memory()
     h_back = {lv: torch.empty(max(total, 16) + 64, dtype=torch.uint8).pin_memory() for lv in LEVELS}
     e2e_steps = max(1, min(args.steps, 3))
-    ms_e2e, calls_e2e = timed(h_px, h_files, h_back, 0, e2e_steps, 1)
+    ms_e2e, calls_e2e = timed(h_px, h_files, h_back, 0, e2e_steps, 1, args.e2e_schedule)
     if n:
         for lv in LEVELS:
             assert np.array_equal(h_back[lv].numpy()[:total], h_px.numpy()[:total]), f"e2e level {lv}: decoded pixels differ"
@@ -411,17 +447,17 @@ def run_ours(args, rank, world, local_rank):
         return out
     breakdown = {"device_sequential": table(calls_dev), "device_sequential_ms_per_step": round(ms_seq / 2, 3),
                  "device_concurrent_levels": table(calls_conc), "e2e": table(calls_e2e),
-                 "note": "value / e2e: the two level jobs run concurrently (one codec context and host thread per level); device_sequential: "
-                         "the same calls one at a time (per-call times without overlap between levels)"}
+                 "note": "value / e2e: a step's levels x parts jobs run on one codec context and host thread each (config.schedule / e2e_schedule); "
+                         "device_sequential: the same calls one at a time (per-call times without overlap, summed over the parts)"}
 
     # ---- level 7 on its own (stored files: a device copy)
     if n:
         t7 = {}
         for _ in range(3):
             t0 = time.perf_counter()
-            offs7, sz7 = cd.encode_raw(7, new_descs(), n, d_px.data_ptr(), total, 1, d_files[1].data_ptr(), cap, 1)
+            offs7, sz7 = cd.encode_raw(7, part_descs(n), n, d_px.data_ptr(), total, 1, d_files[1].data_ptr(), cap, 1)
             t1 = time.perf_counter()
-            cd.decode_raw(new_descs(True), n, d_files[1].data_ptr(), cap, 1, offs7, sz7, d_back[1].data_ptr(), total, 1)
+            cd.decode_raw(part_descs(n, True), n, d_files[1].data_ptr(), cap, 1, offs7, sz7, d_back[1].data_ptr(), total, 1)
             t2 = time.perf_counter()
             t7["enc7"] = min(t7.get("enc7", 1e9), t1 - t0); t7["dec7"] = min(t7.get("dec7", 1e9), t2 - t1)
         npx_shard = n * npx_frame
@@ -431,13 +467,13 @@ def run_ours(args, rank, world, local_rank):
     # ---- per-kernel view of one step (serialised profiling pass, outside the timed region) and the dominant kernel
     per_kernel = {}
     for lv in LEVELS:
+        prof_offs = prof_sz = None
         for what in ("enc", "dec"):
             cd.profile(True)
             if what == "enc":
-                cd.encode_raw(lv, new_descs(), n, d_px.data_ptr(), total, 1, d_files[lv].data_ptr(), cap, 1)
+                prof_offs, prof_sz = cd.encode_raw(lv, part_descs(n), n, d_px.data_ptr(), total, 1, d_files[lv].data_ptr(), cap, 1)
             else:
-                cd.decode_raw(new_descs(True), n, d_files[lv].data_ptr(), cap, 1, (C.c_uint64 * n)(*dev_offs[lv]), (C.c_uint64 * n)(*dev_sizes[lv]),
-                              d_back[lv].data_ptr(), total, 1)
+                cd.decode_raw(part_descs(n, True), n, d_files[lv].data_ptr(), cap, 1, prof_offs, prof_sz, d_back[lv].data_ptr(), total, 1)
             for k, (ms, cnt) in cd.profile_report().items():
                 per_kernel[f"L{lv}.{what}.{k}"] = (ms, cnt, lv)
             cd.profile(False)
@@ -503,7 +539,7 @@ def run_ours(args, rank, world, local_rank):
 
     line = {"metric": METRIC, "value": round(value, 2), "unit": "MPix/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic", "config": workload_config(F, world),
+            "data": "synthetic", "config": dict(workload_config(F, world), parts_per_level=PARTS, schedule=args.schedule, e2e_schedule=args.e2e_schedule),
             "e2e": {"value": round(e2e, 2), "unit": "MPix/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_e2e / e2e_steps, 4), "steps": e2e_steps},
             "gpu_launches": n_launch, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
@@ -521,6 +557,13 @@ def main():
     ap.add_argument("--frames", type=int, default=int(os.environ.get("XPNG_BENCH_FRAMES", "1000")))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parts", type=int, default=int(os.environ.get("XPNG_BENCH_PARTS", "1")),
+                    help="parts a rank's shard is cut into per level; a step runs levels x parts jobs (encode -> decode), one context each "
+                         "(measured: 2 parts cost 28 %% device-resident, calls of 500 frames take almost as long as calls of 1000; 5 %% better end to end)")
+    ap.add_argument("--schedule", default=os.environ.get("XPNG_BENCH_SCHEDULE", "concurrent"), choices=["concurrent", "chained", "sequential"],
+                    help="device-resident leg: all jobs at once / each job's encode starts when the previous job has encoded / one job at a time")
+    ap.add_argument("--e2e-schedule", default=os.environ.get("XPNG_BENCH_E2E_SCHEDULE", "chained"), choices=["concurrent", "chained", "sequential"],
+                    help="host-buffer leg (chained keeps both PCIe directions busy: one job's decode downloads next to the next job's encode uploads)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
