@@ -750,44 +750,50 @@ __device__ __forceinline__ void unpredict_rgb(const UnpredArgs& A, const TileDes
     const uint32_t fp = ld32u(blob + 8);   // first pixel, MSB-first bits
     const uint32_t first = (d->m >> 4) == 2 ? (fp >> 24) * 0x010101u : (((fp >> 24) & 255u) | (((fp >> 16) & 255u) << 8) | (((fp >> 8) & 255u) << 16));
     const uint32_t nbands = (t.h + 31) / 32;
-    constexpr int RING = 16, AHEAD = 12;
+    // Lane r runs FOUR columns behind lane r - 1 (x = s - 4r): every lane is at the same column phase, so the 128-bit
+    // residual load (x = 0 mod 4) and the three-word pixel store (x = 3 mod 4) sit at fixed places of the unrolled loop,
+    // are executed by all lanes at once, and consecutive loads never share a destination register (with a skew of
+    // one column some lanes load at every step, each load waits for the previous one: 13 of 17 cycles per instruction
+    // were long-scoreboard stalls).  U is the upper lane's pixel of four steps ago (static 4-entry history).
+    constexpr int RING = 16, AHEAD = 12, SKEW = 4;
+    const bool tailw = (w & 3u) != 0;
     for (uint32_t b = 0; b < nbands; b++) {
         const uint32_t y = b * 32 + lane;
         const bool rowok = y < t.h, row0 = y == 0;
         const uint32_t lastlane = min(31u, t.h - 1 - b * 32);
         const uint32_t* rrow = res + (uint64_t)y * pitch;            // 16-byte aligned
         uint8_t* orow = dst + (uint64_t)y * t.bpr;                    // word aligned
-        uint32_t left = 0, uprev = 0, prevout = 0, a0 = 0, a1 = 0, a2 = 0;
+        uint32_t left = 0, uprev = 0, a0 = 0, a1 = 0, a2 = 0;
+        uint32_t hist[SKEW] = { 0, 0, 0, 0 };
         uint32_t rn[RING];
 #pragma unroll
         for (int k = 0; k < RING; k++) rn[k] = 0;
-        if (rowok) {   // columns 0 .. 11: column c is consumed at step c + lane, i.e. from slot (c + lane) % RING
+        if (rowok) {   // columns 0 .. 11: column c is consumed at step c + 4 * lane, i.e. from slot (c + 4 * lane) % RING
 #pragma unroll
             for (int g = 0; g < AHEAD / 4; g++) {
                 uint4 v = make_uint4(0, 0, 0, 0);
                 if (4u * g < pitch) v = __ldg(reinterpret_cast<const uint4*>(rrow) + g);
                 const uint32_t vv[4] = { v.x, v.y, v.z, v.w };
+                const uint32_t sb = (4u * g + SKEW * lane) % RING;   // a multiple of 4
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const uint32_t slot = (lane + 4u * g + q) % RING;
+                for (int q = 0; q < 4; q++)
 #pragma unroll
-                    for (int k = 0; k < RING; k++) rn[k] = slot == (uint32_t)k ? vv[q] : rn[k];
-                }
+                    for (int k = 0; k < RING / 4; k++) rn[4 * k + q] = sb == (uint32_t)(4 * k) ? vv[q] : rn[4 * k + q];
             }
         }
-        const uint32_t steps = (w + 31 + RING - 1) / RING * RING;
+        const uint32_t steps = (w + SKEW * 31 + RING - 1) / RING * RING;
         for (uint32_t s0 = 0; s0 < steps; s0 += RING) {
 #pragma unroll
             for (int j = 0; j < RING; j++) {
                 const uint32_t s = s0 + j;
-                const uint32_t x = s - lane;                          // lanes that have not started yet wrap around: x >= w
+                const uint32_t x = s - SKEW * lane;                   // lanes that have not started yet wrap around: x >= w
                 const bool act = rowok && x < w;
                 const uint32_t ub = brow[min(s, w - 1)];              // row above the band (band 0 never uses it)
-                uint32_t U = __shfl_up_sync(0xffffffffu, prevout, 1);
+                uint32_t U = __shfl_up_sync(0xffffffffu, hist[j % SKEW], 1);   // the upper lane's pixel of four steps ago: column x
                 U = lane == 0 ? ub : U;
                 const uint32_t rv = rn[j];
-                {   // refill: at x = 0 (mod 4) the four residuals of columns x + 12 .. x + 15 go to the slots consumed last
-                    const uint32_t go = (act && (x & 3u) == 0 && x + AHEAD < pitch) ? 1u : 0u;
+                if (j % 4 == 0) {   // the four residuals of columns x + 12 .. x + 15 go to the slots consumed last
+                    const uint32_t go = (act && x + AHEAD < pitch) ? 1u : 0u;
                     asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %5, 0;\n @q ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n}"
                                  : "+r"(rn[(j + 12) % RING]), "+r"(rn[(j + 13) % RING]), "+r"(rn[(j + 14) % RING]), "+r"(rn[(j + 15) % RING])
                                  : "l"(rrow + x + AHEAD), "r"(go));
@@ -804,10 +810,10 @@ __device__ __forceinline__ void unpredict_rgb(const UnpredArgs& A, const TileDes
                     // 96-bit shift register: after pixels 4k .. 4k + 3 it holds their twelve bytes in memory order
                     a0 = __funnelshift_r(a0, a1, 24); a1 = __funnelshift_r(a1, a2, 24); a2 = __funnelshift_r(a2, pix, 24);
                     if (lane == lastlane) brow[x] = pix;
-                    if ((x & 3u) == 3u) {
+                    if (j % 4 == 3) {                                 // x = 3 (mod 4) for every lane
                         uint32_t* o = reinterpret_cast<uint32_t*>(orow + 3u * (x - 3u));
                         o[0] = a0; o[1] = a1; o[2] = a2;
-                    } else if (x == w - 1) {                         // 1 .. 3 pixels left over at the row end: byte stores
+                    } else if (tailw && x == w - 1) {                 // 1 .. 3 pixels left over at the row end: byte stores
                         const uint32_t np = (x & 3u) + 1u, sh = 24u * (4u - np);   // bring them down to bit 0 (sh = 24, 48, 72)
                         uint32_t t0 = a0, t1 = a1, t2 = a2;
                         if (sh >= 64) { t0 = t2; t1 = 0; t2 = 0; } else if (sh >= 32) { t0 = t1; t1 = t2; t2 = 0; }
@@ -818,7 +824,7 @@ __device__ __forceinline__ void unpredict_rgb(const UnpredArgs& A, const TileDes
                     }
                 }
                 uprev = U;
-                prevout = pix;
+                hist[j % SKEW] = pix;
             }
         }
         __syncwarp();
