@@ -318,11 +318,12 @@ __global__ void __launch_bounds__(256) k_dec_residuals(ChunkArgs A) {
     uint32_t* res = A.resv + resv_base(t);
     const uint8_t* blob = A.in + d->blob_off;
     const uint32_t e0 = c0 + tid * 16;
-    // destination index of entry e0 and what to add at a row end (0: linear layout)
-    const bool pitched = A.pitched && tile_pitched(t);
-    uint32_t rx = 0, ri = e0, rskip = 0;
-    if (pitched) { const uint32_t ry = (e0 + 1) / t.w; rx = (e0 + 1) - ry * t.w; rskip = ((t.w + 3u) & ~3u) - t.w; ri = ry * (t.w + rskip) + rx; }
-    auto put = [&](uint32_t v) { res[ri] = v; ri++; if (pitched && ++rx == t.w) { rx = 0; ri += rskip; } };
+    // a thread produces 16 consecutive entries; written straight from here they would be 16 word stores 64 bytes apart per
+    // lane (32 sectors per request).  They are staged in shared memory (pitch 17: conflict-free) and leave below with
+    // consecutive lanes on consecutive words.
+    __shared__ uint32_t sres[256 * 17];
+    uint32_t se = tid * 17;
+    auto put = [&](uint32_t v) { sres[se++] = v; };
     uint32_t w[4] = { 0, 0, 0, 0 };
     if (e0 < c1) { const uint4 q = *reinterpret_cast<const uint4*>(seq + e0); w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w; }
     if (MODE == 1) {
@@ -376,6 +377,19 @@ __global__ void __launch_bounds__(256) k_dec_residuals(ChunkArgs A) {
                 else { const uint8_t* q = sbase + so + 3ull * rank; v = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16); }
             }
             put(v);
+        }
+    }
+    __syncthreads();
+    const uint32_t cnt = c1 - c0;
+    if (!(A.pitched && tile_pitched(t))) {
+        for (uint32_t k = tid; k < cnt; k += 256) res[c0 + k] = sres[(k >> 4) * 17 + (k & 15u)];
+    } else {   // row-pitched plane: entry k is pixel k + 1 of the raster
+        const uint32_t w = t.w, pitch = (w + 3u) & ~3u, magic = 0xFFFFFFFFu / w + 1u;   // (p * magic) >> 32 == p / w for p < 2^20
+        for (uint32_t k = tid; k < cnt; k += 256) {
+            const uint32_t p = c0 + k + 1;
+            uint32_t y = w > 1u ? __umulhi(p, magic) : p;
+            if (y * w > p) y--;
+            res[y * pitch + (p - y * w)] = sres[(k >> 4) * 17 + (k & 15u)];
         }
     }
 }

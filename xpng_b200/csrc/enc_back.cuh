@@ -116,6 +116,23 @@ struct CompactArgs {
     const uint8_t* tile_skip;
 };
 
+// n bytes from src to dst, any alignment, by the 256 threads of a CTA: whole destination words are written as words (the
+// source through two aligned words and a funnel shift; reads may touch up to 3 bytes past src + n: every scratch buffer has
+// slack), the bytes around them one by one.  Neighbouring chunks of a stream are written by other CTAs: only bytes of
+// [dst, dst + n) are touched.
+__device__ __forceinline__ void cta_copy_bytes(uint8_t* dst, const uint8_t* src, uint32_t n, uint32_t tid) {
+    const uint32_t head = min(n, (4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
+    if (tid < head) dst[tid] = src[tid];
+    dst += head; src += head; n -= head;
+    const uint32_t nw = n >> 2, sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
+    const uint32_t* s4 = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+    uint32_t* d4 = reinterpret_cast<uint32_t*>(dst);
+    if (sh == 0) for (uint32_t k = tid; k < nw; k += 256) d4[k] = s4[k];
+    else for (uint32_t k = tid; k < nw; k += 256) d4[k] = __funnelshift_r(s4[k], s4[k + 1], sh);
+    const uint32_t tail = n & 3u;
+    if (tid < tail) dst[4u * nw + tid] = src[4u * nw + tid];
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256) k_compact(CompactArgs A) {
     const uint32_t gseg = blockIdx.x, tile = A.seg_tile[gseg], tid = threadIdx.x;
@@ -131,7 +148,7 @@ __global__ void __launch_bounds__(256) k_compact(CompactArgs A) {
     for (int c = 0; c < 9; c++) {
         uint8_t* dst = sbase + st->soff[c] + pl.pos[c];
         const uint32_t n = si.cnt[c];
-        for (uint32_t k = tid; k < n; k += 256) dst[k] = src[so + k];
+        cta_copy_bytes(dst, src + so, n, tid);
         so += n;
     }
     if (tid == 0 && si.has_valid) sbase[st->soff[pl.first_ctx] + pl.first_pos] = si.first_nl;
@@ -143,7 +160,7 @@ __global__ void __launch_bounds__(256) k_compact(CompactArgs A) {
         for (int c = 1; c < 9; c++) {
             uint8_t* dst = sbase + st->soff[8 + c] + vp.pos[c];
             const uint32_t n = (uint32_t)A.vcnt[(uint64_t)gseg * 9 + c] * (c < 3 ? 1u : 3u);
-            for (uint32_t k = tid; k < n; k += 256) dst[k] = vsrc[vo + k];
+            cta_copy_bytes(dst, vsrc + vo, n, tid);
             vo += n;
         }
     }
