@@ -5,5 +5,5 @@ cd "$(dirname "$0")/../xpng_b200"
 name=$1; shift
 mkdir -p build
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC "$@" -c csrc/api.cu -o build/ab_$name.o
-nvcc -shared -o build/ab_$name.so build/ab_$name.o build/xpng_file.o build/seven.o build/png7.o -lz
+nvcc -shared -o build/ab_$name.so build/ab_$name.o build/xpng_file.o build/seven.o build/png7.o build/xpng_pool.o -lz -lpthread -lrt
 echo built build/ab_$name.so

@@ -19,6 +19,12 @@
 
 namespace xpb {
 
+#ifndef F2_MINB1
+#define F2_MINB1 4
+#endif
+#ifndef F2_MINB2
+#define F2_MINB2 2
+#endif
 constexpr int F2_PADPX = 672;                       // pixels staged before the segment's first (>= FRONT2_MAXW + 2, multiple of 16)
 static_assert(F2_PADPX >= (int)FRONT2_MAXW + 2 && F2_PADPX % 16 == 0, "staging pad");
 constexpr int F2_PIXB = (F2_PADPX + SEG) * 3;       // 14304 bytes
@@ -327,7 +333,7 @@ __device__ __forceinline__ void front2_segment(const FrontArgs& A, Front2Shared&
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(FRONT_THREADS, MODE == 1 ? 3 : 2) k_front2(FrontArgs A) {
+__global__ void __launch_bounds__(FRONT_THREADS, MODE == 1 ? F2_MINB1 : F2_MINB2) k_front2(FrontArgs A) {
     __shared__ __align__(16) Front2Shared S;
     const uint32_t gseg = blockIdx.x, tile = A.seg_tile[gseg];
     const TileDesc t = A.tiles[tile];
