@@ -66,7 +66,7 @@ struct xpngb_ctx {
     uint32_t direct_max_tiles = 148;  // level-2 decode: tiles per call up to which the 64 KiB direct tables are used (3 chains per SM stay resident)
     uint32_t v2_direct_max_tiles = ~0u;  // level-1 decode: same trade for the 16 KiB context tables
     uint32_t unr_multi_max_tiles = 592, unr_force = 0;   // un-predict: tiles per call up to which a tile gets 8 warps; XPNGB_UNR_NW forces a variant (A/B)
-    uint32_t lat_max_blocks = 32768;  // decode: entropy blocks per call up to which the warp-per-block (latency) kernels are used (measured crossover, profiles/)
+    uint32_t lat_max_blocks = 12000;  // decode: entropy blocks per call up to which the warp-per-block (latency) kernels are used (measured crossover, profiles/)
     uint32_t enc_lat_max_blocks = ~0u; // encode: the pair-lane encoders serve every batch size (chunks in flight keep their launches resident)
     // device scratch
     DevBuf pixels, norm, files, arena, tiles, imgs, seg_tile, costs, hist, seginfo, place, vplace, vcnt, sym_area,
@@ -478,12 +478,21 @@ static std::vector<uint32_t> cut_chunks(const xpngb_ctx* ctx, const xpngb_image*
     uint64_t want = (total + ctx->pipe_lanes - 1) / ctx->pipe_lanes;
     if (want < ctx->pipe_min_px) want = ctx->pipe_min_px;
     if (want > ctx->max_chunk_px) want = ctx->max_chunk_px;
+    // k chunks of equal share: chunk c ends with the image that brings the running pixel count to (c + 1) / k of the total.
+    // (Cutting whenever `want` pixels are exceeded leaves a small extra chunk when the images do not divide evenly, and a
+    // chunk beyond the lanes waits for a lane: a whole chain latency for a handful of images.)
+    uint64_t k = (total + want - 1) / want;
+    if (k < 1) k = 1;
+    if (k > n) k = n;
     std::vector<uint32_t> cuts{ 0 };
-    uint64_t px = 0;
-    for (uint32_t i = 0; i < n; i++) {
-        const uint64_t p = imgs[i].w * imgs[i].h;
-        if (px && px + p > want) { cuts.push_back(i); px = 0; }
-        px += p;
+    uint64_t px = 0, c = 1;
+    for (uint32_t i = 0; i < n && c < k; i++) {
+        px += imgs[i].w * imgs[i].h;
+        typedef unsigned __int128 u128;   // w, h <= 2^24 each: the products exceed 64 bits for absurd batches only, but must not wrap
+        if ((u128)px * k >= (u128)c * total && i + 1 < n) {
+            cuts.push_back(i + 1);
+            while (c < k && (u128)px * k >= (u128)c * total) c++;
+        }
     }
     cuts.push_back(n);
     return cuts;
