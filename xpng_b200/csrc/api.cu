@@ -66,6 +66,7 @@ struct xpngb_ctx {
     uint32_t direct_max_tiles = 148;  // level-2 decode: tiles per call up to which the 64 KiB direct tables are used (3 chains per SM stay resident)
     uint32_t v2_direct_max_tiles = ~0u;  // level-1 decode: same trade for the 16 KiB context tables
     uint32_t unr_multi_max_tiles = 592, unr_force = 0;   // un-predict: tiles per call up to which a tile gets 8 warps; XPNGB_UNR_NW forces a variant (A/B)
+    uint32_t s16_lat_max_tiles = 1776;  // level-2 decode, pair family: calls up to this many tiles decode the 16-symbol value stream (the longest chain) warp-per-block
     uint32_t lat_max_blocks = 12000;  // decode: entropy blocks per call up to which the warp-per-block (latency) kernels are used (measured crossover, profiles/)
     uint32_t enc_lat_max_blocks = ~0u; // encode: the pair-lane encoders serve every batch size (chunks in flight keep their launches resident)
     // device scratch
@@ -111,15 +112,17 @@ struct xpngb_ctx {
 // time; the data-parallel kernels of the other chunks in flight fill the machine.  The block scheduler serves streams
 // of higher priority first, so chains go to high-priority streams: their CTAs become resident as soon as they are
 // launched instead of queueing behind hundreds of thousands of front-end CTAs.
-static cudaStream_t prio_stream(const xpngb_ctx* ctx) {
+// level 0: the longest chains of a call (side stream 0: the 16-symbol value streams of level 2), level 1: other chains.
+static cudaStream_t prio_stream(const xpngb_ctx* ctx, int level) {
     cudaStream_t s = nullptr;
-    int lo = 0, hi = 0;
-    if (ctx->root->use_prio && cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess && hi != lo) cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi);
+    int lo = 0, hi = 0;   // numerically lower = served first
+    if (ctx->root->use_prio && cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess && hi != lo)
+        cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, (hi + level < lo) ? hi + level : hi);
     else cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
     return s;
 }
 static cudaStream_t side_of(xpngb_ctx* ctx, int k) {
-    if (!ctx->side[k]) ctx->side[k] = prio_stream(ctx);   // side streams only ever carry chains
+    if (!ctx->side[k]) ctx->side[k] = prio_stream(ctx, k == 0 ? 0 : 1);   // side streams only ever carry chains
     return ctx->side[k];
 }
 #define LAUNCH_HI(kernel, grid, block, smem, ...)                                                   \
@@ -127,7 +130,7 @@ static cudaStream_t side_of(xpngb_ctx* ctx, int k) {
         cudaStream_t base_ = ctx->cur;                                                              \
         const bool tw_ = base_ == ctx->stream && ctx->root->use_prio && (ctx->root->profile == 0 || ctx->root->profile == 3);       \
         if (tw_) {                                                                                  \
-            if (!ctx->hi) ctx->hi = prio_stream(ctx);                                               \
+            if (!ctx->hi) ctx->hi = prio_stream(ctx, 1);                                               \
             CK(cudaEventRecord(ctx->ev_hi, base_)); CK(cudaStreamWaitEvent(ctx->hi, ctx->ev_hi, 0)); ctx->cur = ctx->hi; \
         }                                                                                           \
         LAUNCH(kernel, grid, block, smem, __VA_ARGS__);                                             \
@@ -412,6 +415,7 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     { auto k_big = k_rans_v2<256, 32>; cudaFuncSetAttribute(k_big, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * 32 * 16); }
     m2_set_attributes();
     if (const char* e = getenv("XPNGB_LAT_MAX_BLOCKS")) ctx->lat_max_blocks = (uint32_t)atol(e);
+    if (const char* e = getenv("XPNGB_S16_LAT_MAX_TILES")) ctx->s16_lat_max_tiles = (uint32_t)atol(e);
     if (const char* e = getenv("XPNGB_ENC_LAT_MAX_BLOCKS")) ctx->enc_lat_max_blocks = (uint32_t)atol(e);
     if (const char* e = getenv("XPNGB_V2_DIRECT_MAX_TILES")) ctx->v2_direct_max_tiles = (uint32_t)atol(e);
     if (const char* e = getenv("XPNGB_WALK")) { ctx->walk_global = !strcmp(e, "global"); ctx->walk_ring = !strcmp(e, "ring"); }
@@ -1117,6 +1121,13 @@ static int decode_issue(xpngb_ctx* ctx, bool lat, xpngb_image* imgs, uint32_t n,
             PdFillArgs fa{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, (uint8_t*)ctx->alpha.p, ntiles, 2 };
             auto k_dec_rans_pair_v1_s16 = k_dec_rans_pair<1, 15>; auto k_dec_rans_pair_v1_big = k_dec_rans_pair<1, 0>; auto k_dec_rans_pair_v1_s8 = k_dec_rans_pair<1, 8>;
             FORK_SIDE(0); side_busy[0] = true;
+            if (call_tiles <= ctx->root->s16_lat_max_tiles) {
+                // few enough of the longest chains to be resident all at once as warp-per-block chains with a two-level table
+                // (about 55 cycles per symbol, against about 170 per symbol and state of the pair decoder)
+                RansV1LatArgs la{ d_tiles, d_imgs, d_dt, din, (uint8_t*)ctx->streams.p, ntiles, 0, 1, LUT_TWO_14, 0u, ~0u, d_err };
+                auto k_dec_rans_v1_lat_st4 = k_dec_rans_v1_lat;
+                LAUNCH_HI(k_dec_rans_v1_lat_st4, ntiles, 32, lat_smem(LUT_TWO_14), la);
+            } else
             LAUNCH_HI(k_dec_rans_pair_v1_s16, pd_grid(1), PD_WARPS * 32, 0, pd_args(W, PD_S16));
             FORK_SIDE(1); side_busy[1] = true;
             LAUNCH_HI(k_dec_rans_pair_v1_big, pd_grid(5), PD_WARPS * 32, PD_WARPS * PD_BIG_BYTES, pd_args(W, PD_BIG));
@@ -1127,7 +1138,7 @@ static int decode_issue(xpngb_ctx* ctx, bool lat, xpngb_image* imgs, uint32_t n,
         if (launch_walk(2)) return 1;
     }
     // batches: RGB tiles with word-aligned rows get the row-pitched residual plane and k_dec_unpredict_rgb
-    const uint32_t pitched = (!lat && !ctx->root->unr_force) ? 1u : 0u;
+    const uint32_t pitched = ((!lat || call_tiles > ctx->root->unr_multi_max_tiles) && !ctx->root->unr_force) ? 1u : 0u;
     bool all_pitched = true;
     for (const TileDesc& t : P.tiles) all_pitched &= tile_pitched(t);
     if (any1 || any2) {
@@ -1206,7 +1217,9 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
         if (mode == 1 || mode == 2) tiles_est += (dims[i].w * dims[i].h + TILE_AREA - 1) / TILE_AREA;
         l2 |= mode == 2;
     }
-    const bool lat = l2 ? 17 * tiles_est <= (uint64_t)ctx->lat_max_blocks * 5 / 2 : 9 * tiles_est <= ctx->lat_max_blocks;
+    // level 2: above ~600 tiles the pair family wins, with the 16-symbol value streams warp-per-block while they all fit
+    // (s16_lat_max_tiles); level 1: the warp-per-block family up to ~1300 tiles (measured at 125 / 250 / 500 frames, profiles/)
+    const bool lat = l2 ? 17 * tiles_est <= (uint64_t)ctx->lat_max_blocks * 5 / 6 : 9 * tiles_est <= ctx->lat_max_blocks;
     const std::vector<uint32_t> cuts = cut_chunks(ctx, dims.data(), n);
     const uint32_t nchunks = (uint32_t)cuts.size() - 1;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
