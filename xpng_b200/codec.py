@@ -106,6 +106,11 @@ class Codec:
         self._h = C.c_void_p()
         if lib().xpngb_create(C.byref(self._h), int(device)):
             raise RuntimeError("xpngb_create failed: no usable CUDA device (there is no CPU fallback)")
+        # CUDA is initialised now: the queue count asked for in __init__.py has been read, children need not inherit it
+        import xpng_b200 as _pkg
+        if getattr(_pkg, "CONNECTIONS_SET_HERE", False):
+            os.environ.pop("CUDA_DEVICE_MAX_CONNECTIONS", None)
+            _pkg.CONNECTIONS_SET_HERE = False
 
     def close(self):
         if self._h:

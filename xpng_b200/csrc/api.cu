@@ -399,10 +399,10 @@ static xpngb_ctx* lane_get(xpngb_ctx* root, uint32_t i) {
 extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     if (!out) return 1;
     *out = nullptr;
-    // a call keeps up to pipe_lanes x 3 streams busy; the driver's default of 8 hardware queues would make them wait on each
-    // other (false dependencies).  Read by the driver when it initialises, so this only acts in a process that has not
-    // touched CUDA yet; hosts that initialise CUDA first set it themselves.
-    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    // A batch call keeps up to pipe_lanes x 3 streams busy: hosts that code batches export CUDA_DEVICE_MAX_CONNECTIONS=32
+    // before their first CUDA call (the driver's default of 8 hardware queues makes the streams of a call
+    // wait on each other).  It is not forced here: 32 queues add ~2.5 s to every process start, which a one-image CLI run
+    // should not pay (tools/ctx_time.py).
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return 1;
     if (cudaSetDevice(device) != cudaSuccess) return 1;
