@@ -139,6 +139,25 @@ def test_file_api_and_cli_against_reference(codec, tmp_path):
                 assert np.array_equal(codec.decode([po.ref_encode(lv, px)])[0], po.normalize(px))
 
 
+def test_file_api_is_reentrant(codec, tmp_path):
+    """xpng_store / xpng_load from several host threads at once (the reference keeps no global mutable state):
+    every caller takes its own codec context from the library's pool; results equal the oracle's."""
+    import xpng_b200
+    from concurrent.futures import ThreadPoolExecutor
+    imgs = [synth.rgb(200 + 37 * k, 300 + 11 * k, 90 + k) for k in range(6)] + [synth.rgba(180, 260, 97)]
+
+    def job(k):
+        px, lv, fn = imgs[k], 1 + (k & 1), str(tmp_path / f"t{k}.xpng")
+        for _ in range(3):
+            assert xpng_b200.xpng_store(lv, px, fn) is False
+            assert open(fn, "rb").read() == po.encode(lv, px)
+            assert np.array_equal(xpng_b200.xpng_load(fn), po.normalize(px))
+        return True
+
+    with ThreadPoolExecutor(len(imgs)) as pool:
+        assert all(pool.map(job, range(len(imgs))))
+
+
 def test_ycocg_r_side_kernel(codec):
     """Tell_Me_Why/YCoCg-R.c: exhaustive 2^24 reversibility and ranges, on the device."""
     r, g, b = np.meshgrid(np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), np.arange(256, dtype=np.uint8), indexing="ij")
@@ -248,6 +267,45 @@ def test_fuzzed_files_never_crash(codec):
             except RuntimeError:
                 pass
         assert np.array_equal(codec.decode([good])[0], po.normalize(img))
+
+
+def _level2_with_oversized_value_blocks(img):
+    """A valid single-tile level-2 file whose eight value blocks (st1..st8, App. A.5) are replaced by type-1 runs that each
+    claim 3 * npx symbols: every block passes a per-block bound, their sum is far beyond the tile's stream slice."""
+    import struct
+    f = po.encode(2, img)
+    h, w = img.shape[:2]
+    assert (struct.unpack_from("<I", f, 0)[0] >> 24) == 2
+    t0 = 8
+    tw = struct.unpack_from("<I", f, t0)[0]
+    assert (tw >> 24) & 0xF0 == 0x10 and (tw & 0xFFFFFF) == len(f) - 8       # one coded RGB tile
+    bsz = struct.unpack_from("<I", f, t0 + 4)[0]
+    p = t0 + 4 + bsz                                                          # first of the 17 v1 blocks
+    for _ in range(9):                                                        # keep the nine context blocks
+        p += struct.unpack_from("<I", f, p)[0] & 0xFFFFFF
+    body = bytearray(f[:p])
+    for _ in range(8):                                                        # type 1: [8 | 1 << 24][n | sym << 24]
+        body += struct.pack("<II", 8 | (1 << 24), (3 * w * h) | (5 << 24))
+    struct.pack_into("<I", body, t0, (len(body) - 8) | (tw & 0xFF000000))
+    return bytes(body)
+
+
+def test_crafted_value_block_counts_are_rejected(codec):
+    """the running stream offset of a level-2 tile must be bounded, not only each block."""
+    img = synth.rgb(96, 128, 77)
+    bad = _level2_with_oversized_value_blocks(img)
+    for fam in ("0", "10000000"):                      # both decoder families
+        os.environ["XPNGB_LAT_MAX_BLOCKS"] = fam
+        try:
+            import xpng_b200
+            cd = xpng_b200.Codec(0)
+            with pytest.raises(RuntimeError):
+                cd.decode([bad])
+            # the context is still healthy and nothing outside the tile's slice was written: a clean decode follows
+            assert np.array_equal(cd.decode([po.encode(2, img)])[0], img)
+            cd.close()
+        finally:
+            del os.environ["XPNGB_LAT_MAX_BLOCKS"]
 
 
 def test_thin_tiles_first_in_batch(codec):
