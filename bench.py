@@ -211,26 +211,25 @@ def run_reference(args, rank, world):
     per_step, calls, kind, cores, how = reference_steps(frames, steps, args.warmup)
     npx = nf * FW * FH
     value = 4 * npx / 1e6 / per_step
-    sample = f"first {nf} of the {args.frames} frames, levels 1 and 2, encode then decode of every frame per level, {how}"
+    sample = (f"first {nf} of the {args.frames} frames of the same batch (config is the GPU arm's; the CPU arm codes a bounded sample), "
+              f"levels 1 and 2, encode then decode of every frame per level, {how}")
     line = {"metric": METRIC, "value": round(value, 2), "unit": "MPix/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
             "ms_per_step": round(per_step * 1e3, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "impl": "reference",
-            "config": workload_config(args.frames, world, sample_frames=nf),
+            "config": dict(workload_config(args.frames, world), parts_per_level=max(1, args.parts), schedule=args.schedule, e2e_schedule=args.e2e_schedule),
             "cpu_baseline": {"value": round(value, 2), "unit": "MPix/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": round(value, 2), "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "breakdown": call_table(calls, npx)}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(frames, world, sample_frames=None):
+def workload_config(frames, world):
     cfg = {"workload": f"configs[2]: {frames} sintel-like 1920x1080 RGB frames (seeds {SEED0}..{SEED0 + frames - 1}), levels -1/-2, "
                        "encode + size/offset gather + decode per level",
            "frames": frames, "tiles_per_frame": 8,
            "l2": "no flush needed: a rank's pixels, files and scratch are far larger than the 126 MB L2 (>= 0.7 GB per rank at N = 8)",
            "parallelism": f"frames sharded contiguously over {world} GPU(s) (xpngb_shard_range), no data-path collective; "
                           "one shared-memory size gather per level (xpngb_gather_sizes, C, no NCCL)"}
-    if sample_frames is not None:
-        cfg["reference_sample_frames"] = sample_frames
     return cfg
 
 
