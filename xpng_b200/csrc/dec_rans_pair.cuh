@@ -250,16 +250,19 @@ __global__ void __launch_bounds__(PD_WARPS * 32) k_dec_rans_pair(PairDecArgs A) 
 
     // ---- ring staging by the whole warp
     uint32_t staged = 0, k = 0;
-    auto fetch = [&](uint32_t bi, uint32_t& s0) -> uint32_t {       // 32 words of block bi starting at its `staged`
+    struct Raw { uint32_t a0, a1, z, s0; bool in; };                // a refill in flight: two aligned words per lane, not yet combined
+    auto fetch = [&](uint32_t bi) -> Raw {                          // 32 words of block bi starting at its `staged`
         const uint4 src = s_src[wid][bi];
         const uint32_t* base = reinterpret_cast<const uint32_t*>(((uint64_t)src.y << 32) | src.x);
-        s0 = __shfl_sync(0xffffffffu, staged, 2 * bi);
-        const uint32_t nw = src.w, kk = s0 + lane, kc = min(kk, nw ? nw - 1u : 0u);
-        uint32_t a0, a1;
-        if (VER == 1) { const uint32_t jmax = src.z ? nw : (nw ? nw - 1u : 0u); a0 = __ldg(base + kc); a1 = __ldg(base + min(kc + 1u, jmax)); }
-        else { a0 = __ldg(base - kc); a1 = __ldg(base - kc + 1); }
-        return kk < nw ? __funnelshift_r(a0, a1, src.z) : 0u;
+        Raw f; f.z = src.z;
+        f.s0 = __shfl_sync(0xffffffffu, staged, 2 * bi);
+        const uint32_t nw = src.w, kk = f.s0 + lane, kc = min(kk, nw ? nw - 1u : 0u);
+        if (VER == 1) { const uint32_t jmax = src.z ? nw : (nw ? nw - 1u : 0u); f.a0 = __ldg(base + kc); f.a1 = __ldg(base + min(kc + 1u, jmax)); }
+        else { f.a0 = __ldg(base - kc); f.a1 = __ldg(base - kc + 1); }
+        f.in = kk < nw;
+        return f;
     };
+    auto word = [](const Raw& f) -> uint32_t { return f.in ? __funnelshift_r(f.a0, f.a1, f.z) : 0u; };   // first use of the loaded registers
     auto land = [&](uint32_t bi, uint32_t s0, uint32_t v) {
         const uint32_t slot = (s0 + lane) & (PD_RING - 1u);
         ring[slot * PD_BLK + bi] = v;
@@ -268,11 +271,11 @@ __global__ void __launch_bounds__(PD_WARPS * 32) k_dec_rans_pair(PairDecArgs A) 
     };
     for (uint32_t rep = 0; rep < 2; rep++)
         for (uint32_t bi = 0; bi < PD_BLK; bi += 4) {                // four loads in flight per lane
-            uint32_t s0[4], v[4];
+            Raw f[4];
 #pragma unroll
-            for (int q = 0; q < 4; q++) v[q] = fetch(bi + q, s0[q]);
+            for (int q = 0; q < 4; q++) f[q] = fetch(bi + q);
 #pragma unroll
-            for (int q = 0; q < 4; q++) land(bi + q, s0[q], v[q]);
+            for (int q = 0; q < 4; q++) land(bi + q, f[q].s0, word(f[q]));
         }
     __syncwarp();
 
@@ -300,10 +303,10 @@ __global__ void __launch_bounds__(PD_WARPS * 32) k_dec_rans_pair(PairDecArgs A) 
         uint32_t s = 0, f, bias;
         if (!BIG) {
             const uint32_t s2 = (slot * 0x00010001u) | 0x80008000u;
-            uint32_t r = 0;
+            uint32_t r = 0, r1 = 0;                                   // two accumulation chains: half the dependent depth
 #pragma unroll
-            for (int q = 0; q < NP; q++) r |= ((s2 - tp[q]) >> q) & (0x80008000u >> q);
-            s = (uint32_t)__popc(r);
+            for (int q = 0; q < NP; q++) { const uint32_t bit = ((s2 - tp[q]) >> q) & (0x80008000u >> q); if (q & 1) r1 |= bit; else r |= bit; }
+            s = (uint32_t)__popc(r | r1);
             const uint32_t e = fsb[s * PD_BLK];
             f = e >> 16; bias = slot - (e & 0xFFFFu);
         } else {
@@ -322,18 +325,20 @@ __global__ void __launch_bounds__(PD_WARPS * 32) k_dec_rans_pair(PairDecArgs A) 
         k += (uint32_t)__popc(bal & pairmask);
         return s;
     };
-    // words are staged ahead of the chain: land the refill requested at the previous check, request the next one
-    uint32_t pend = 32, pend_s0 = 0, pend_v = 0;
+    // words are staged ahead of the chain: land the refill requested at the previous check, request the next one.  The
+    // loaded registers are first touched when they land, eight rounds after the loads were issued (combining them in the
+    // same check made the warp wait for global memory at every check: 31 % of the stall samples of the kernel, ncu r02z)
+    uint32_t pend = 32; Raw pf; pf.a0 = pf.a1 = pf.z = pf.s0 = 0; pf.in = false;
     auto check = [&]() {
-        if (pend < 32) { land(pend, pend_s0, pend_v); __syncwarp(); pend = 32; }
+        if (pend < 32) { land(pend, pf.s0, word(pf)); __syncwarp(); pend = 32; }
         uint32_t needy = __ballot_sync(0xffffffffu, h == 0 && staged < nwords && staged < k + PD_LOW);
-        while (needy) {
+        while (needy & (needy - 1u)) {                              // several blocks at once (rare): all but the last are served on the spot
             const uint32_t bi = (__ffs(needy) - 1) >> 1;
             needy &= needy - 1;
-            uint32_t s0; const uint32_t v = fetch(bi, s0);
-            if (needy) { land(bi, s0, v); __syncwarp(); }           // several blocks at once (rare): served on the spot
-            else { pend = bi; pend_s0 = s0; pend_v = v; }
+            const Raw f = fetch(bi);
+            land(bi, f.s0, word(f)); __syncwarp();
         }
+        if (needy) { pend = (__ffs(needy) - 1) >> 1; pf = fetch(pend); }   // loaded straight into the pending registers: no move may wait for them
     };
     // a group = 8 symbols of the block = 4 rounds; lane h keeps the symbols at offsets h, h + 2, h + 4, h + 6 of the group
     auto emit8 = [&](uint32_t m, uint8_t* dst, bool on) {
