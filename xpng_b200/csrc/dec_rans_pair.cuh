@@ -7,8 +7,10 @@
 // of a round are read from a shared-memory ring before the round starts (k is known from the previous round).
 // Symbol search is a compare-accumulate over per-lane thresholds held in registers (alphabets of at most 16 symbols;
 // larger alphabets: per-block cumulative table + 256-entry coarse index in shared memory).  The renormalisation
-// words of the 16 blocks are staged by the WHOLE warp, 32 consecutive words of one block per refill (one coalesced
-// load), issued at one check and stored at the next, so that its memory latency never meets the chains.
+// words of the 16 blocks are staged by the WHOLE warp, 32 consecutive ALIGNED words of one block per refill, copied
+// global -> shared by cp.async (no register ever waits for global memory; any number of blocks per check); a block's
+// byte misalignment is removed by a funnel shift of neighbouring ring words when the chain reads them, off its
+// dependent path.  Copies issued at one check are awaited at the next, eight rounds later.
 // Blocks are handed out from a work list sorted by symbol count (k_pd_*), so that the 16 blocks of a warp end together.
 //
 // The warp-per-block kernels of dec_rans_lat.cuh (41 cycles per symbol, but one useful lane in 32) stay the latency
@@ -154,7 +156,7 @@ template <int VER, int NTH>
 __global__ void __launch_bounds__(PD_WARPS * 32) k_dec_rans_pair(PairDecArgs A) {
     constexpr bool BIG = NTH == 0;
     constexpr int NTHR = BIG ? 1 : NTH;
-    __shared__ uint32_t s_ring[PD_WARPS][(PD_RING + 1) * PD_BLK];   // slot 0 is mirrored behind the ring: word k + 1 never needs a wrap
+    __shared__ uint32_t s_ring[PD_WARPS][(PD_RING + 2) * PD_BLK];   // aligned words; slots 0 and 1 are mirrored behind the ring: words k + 1, k + 2 never need a wrap
     __shared__ uint4 s_src[PD_WARPS][PD_BLK];                       // word source: aligned base (lo, hi), 8 * misalignment, words
     __shared__ uint32_t s_fs[BIG ? 1 : PD_WARPS][BIG ? 1 : (NTH + 1) * PD_BLK];   // [symbol][block]: start | freq << 16
     extern __shared__ __align__(16) uint8_t s_big[];                // BIG: [PD_WARPS][PD_BIG_BYTES]
@@ -248,35 +250,28 @@ __global__ void __launch_bounds__(PD_WARPS * 32) k_dec_rans_pair(PairDecArgs A) 
     }
     __syncwarp();
 
-    // ---- ring staging by the whole warp
+    // ---- ring staging by the whole warp: slot j of a block holds its aligned word j (VER 1: base[j]; VER 2: base[1 - j],
+    // the words run downwards); stream word k is the funnel shift of slots k and k + 1
     uint32_t staged = 0, k = 0;
-    struct Raw { uint32_t a0, a1, z, s0; bool in; };                // a refill in flight: two aligned words per lane, not yet combined
-    auto fetch = [&](uint32_t bi) -> Raw {                          // 32 words of block bi starting at its `staged`
+    const uint32_t nraw = nwords + 1u;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
+    auto stage = [&](const uint32_t bi) {                          // 32 aligned words of block bi from its `staged` on (all lanes)
         const uint4 src = s_src[wid][bi];
         const uint32_t* base = reinterpret_cast<const uint32_t*>(((uint64_t)src.y << 32) | src.x);
-        Raw f; f.z = src.z;
-        f.s0 = __shfl_sync(0xffffffffu, staged, 2 * bi);
-        const uint32_t nw = src.w, kk = f.s0 + lane, kc = min(kk, nw ? nw - 1u : 0u);
-        if (VER == 1) { const uint32_t jmax = src.z ? nw : (nw ? nw - 1u : 0u); f.a0 = __ldg(base + kc); f.a1 = __ldg(base + min(kc + 1u, jmax)); }
-        else { f.a0 = __ldg(base - kc); f.a1 = __ldg(base - kc + 1); }
-        f.in = kk < nw;
-        return f;
-    };
-    auto word = [](const Raw& f) -> uint32_t { return f.in ? __funnelshift_r(f.a0, f.a1, f.z) : 0u; };   // first use of the loaded registers
-    auto land = [&](uint32_t bi, uint32_t s0, uint32_t v) {
-        const uint32_t slot = (s0 + lane) & (PD_RING - 1u);
-        ring[slot * PD_BLK + bi] = v;
-        if (slot == 0) ring[PD_RING * PD_BLK + bi] = v;
+        const uint32_t s0 = __shfl_sync(0xffffffffu, staged, 2 * bi);
+        const uint32_t nw = src.w, j = s0 + lane;
+        const uint32_t* p;                                          // clamped to the words the block owns (slots past them are never consumed by a valid stream)
+        if (VER == 1) { const uint32_t jmax = src.z ? nw : (nw ? nw - 1u : 0u); p = base + min(j, jmax); }
+        else p = base + 1 - (int64_t)min(j, nw);
+        const uint32_t slot = j & (PD_RING - 1u);
+        const uint32_t dst = ring_s + (slot * PD_BLK + bi) * 4u;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(p) : "memory");
+        if (slot < 2u) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst + PD_RING * PD_BLK * 4u), "l"(p) : "memory");
         if (blk == bi) staged += 32;
     };
     for (uint32_t rep = 0; rep < 2; rep++)
-        for (uint32_t bi = 0; bi < PD_BLK; bi += 4) {                // four loads in flight per lane
-            Raw f[4];
-#pragma unroll
-            for (int q = 0; q < 4; q++) f[q] = fetch(bi + q);
-#pragma unroll
-            for (int q = 0; q < 4; q++) land(bi + q, f[q].s0, word(f[q]));
-        }
+        for (uint32_t bi = 0; bi < PD_BLK; bi++) stage(bi);
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
 
     // ---- the recurrences
@@ -298,7 +293,10 @@ __global__ void __launch_bounds__(PD_WARPS * 32) k_dec_rans_pair(PairDecArgs A) 
     const uint32_t otmask = 1u << (lane ^ 1u), pairmask = 3u << (lane & 30u);
     auto round = [&](const bool act, const bool first) -> uint32_t {   // one symbol of my state; first: my state precedes the partner's in this round
         const uint32_t kb = (k & (PD_RING - 1u)) * (PD_BLK * 4u);
-        const uint32_t c0 = *reinterpret_cast<const uint32_t*>(ringb + kb), c1 = *reinterpret_cast<const uint32_t*>(ringb + kb + PD_BLK * 4u);
+        const uint32_t r0 = *reinterpret_cast<const uint32_t*>(ringb + kb), r1 = *reinterpret_cast<const uint32_t*>(ringb + kb + PD_BLK * 4u),
+                       r2 = *reinterpret_cast<const uint32_t*>(ringb + kb + PD_BLK * 8u);
+        const uint32_t c0 = VER == 1 ? __funnelshift_r(r0, r1, sh) : __funnelshift_r(r1, r0, sh);   // stream words k and k + 1
+        const uint32_t c1 = VER == 1 ? __funnelshift_r(r1, r2, sh) : __funnelshift_r(r2, r1, sh);
         const uint32_t slot = xlo & mask;
         uint32_t s = 0, f, bias;
         if (!BIG) {
@@ -325,20 +323,17 @@ __global__ void __launch_bounds__(PD_WARPS * 32) k_dec_rans_pair(PairDecArgs A) 
         k += (uint32_t)__popc(bal & pairmask);
         return s;
     };
-    // words are staged ahead of the chain: land the refill requested at the previous check, request the next one.  The
-    // loaded registers are first touched when they land, eight rounds after the loads were issued (combining them in the
-    // same check made the warp wait for global memory at every check: 31 % of the stall samples of the kernel, ncu r02z)
-    uint32_t pend = 32; Raw pf; pf.a0 = pf.a1 = pf.z = pf.s0 = 0; pf.in = false;
+    // words are staged ahead of the chain: the copies requested at the previous check (eight rounds ago) are complete and
+    // made visible to the warp, then every block with fewer than PD_LOW words ahead gets its next 32
     auto check = [&]() {
-        if (pend < 32) { land(pend, pf.s0, word(pf)); __syncwarp(); pend = 32; }
-        uint32_t needy = __ballot_sync(0xffffffffu, h == 0 && staged < nwords && staged < k + PD_LOW);
-        while (needy & (needy - 1u)) {                              // several blocks at once (rare): all but the last are served on the spot
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        uint32_t needy = __ballot_sync(0xffffffffu, h == 0 && staged < nraw && staged < k + PD_LOW);
+        while (needy) {
             const uint32_t bi = (__ffs(needy) - 1) >> 1;
             needy &= needy - 1;
-            const Raw f = fetch(bi);
-            land(bi, f.s0, word(f)); __syncwarp();
+            stage(bi);
         }
-        if (needy) { pend = (__ffs(needy) - 1) >> 1; pf = fetch(pend); }   // loaded straight into the pending registers: no move may wait for them
     };
     // a group = 8 symbols of the block = 4 rounds; lane h keeps the symbols at offsets h, h + 2, h + 4, h + 6 of the group
     auto emit8 = [&](uint32_t m, uint8_t* dst, bool on) {

@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_dec_walk3(WalkArgs A, const uint
     const TileDesc t = A.tiles[tile];
     const DecTile* d = A.dt + tile;
     uint8_t* out = A.nlseq + t.px_off;
+    asm volatile("" : "+l"(out));                            // held in registers: rebuilt from the parameter bank at every store group, the add waited for the constant load (13 % of the stall samples, ncu r03c)
     const uint32_t m = exists ? d->nsym : 0u;
     uint32_t mmax = m;
 #pragma unroll
