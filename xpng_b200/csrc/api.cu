@@ -48,6 +48,8 @@ struct xpngb_ctx {
     bool use_prio = true;                      // root: XPNGB_PRIO=0 switches the priorities off (A/B)
     cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, pe0 = nullptr, pe1 = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_stage = nullptr;            // decode: this lane's chunk has finished its context-decode (or walk) phase (staggered waves)
+    uint32_t dec_stagger1 = 0, dec_stagger2 = 0, dec_stagger_at = 0;   // root: XPNGB_DEC_STAGGER1/2 = S: chunk k of a level-1/2 batch decode starts when chunk k - S has passed its stage (0: all at once); XPNGB_DEC_STAGGER_AT: 0 contexts decoded, 1 walked
     int profile = 0;   // 1: per-kernel CUDA-event timing accumulated (serialises the launches); 2: also print to stderr;
                        // 3: timeline — start/end of every launch relative to the call's start, launches NOT serialised (stderr)
     int lane_id = 0;
@@ -361,7 +363,7 @@ static void lane_free(xpngb_ctx* ctx) {
     if (ctx->pin_b.p) cudaFreeHost(ctx->pin_b.p);
     if (ctx->pin_o.p) cudaFreeHost(ctx->pin_o.p);
     if (ctx->hi) { cudaStreamSynchronize(ctx->hi); cudaStreamDestroy(ctx->hi); }
-    cudaEvent_t evs[] = { ctx->ev0, ctx->ev1, ctx->ev_fork, ctx->pe0, ctx->pe1, ctx->ev_done, ctx->ev_hi };
+    cudaEvent_t evs[] = { ctx->ev0, ctx->ev1, ctx->ev_fork, ctx->pe0, ctx->pe1, ctx->ev_done, ctx->ev_hi, ctx->ev_stage };
     for (cudaEvent_t e : evs) if (e) cudaEventDestroy(e);
     for (int k = 0; k < xpngb_ctx::NSIDE; k++) { if (ctx->ev_join[k]) cudaEventDestroy(ctx->ev_join[k]); if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -375,6 +377,7 @@ static xpngb_ctx* lane_new(int device, xpngb_ctx* root) {
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_stage, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&ctx->ev_hi, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess &&
               cudaEventCreate(&ctx->pe0) == cudaSuccess && cudaEventCreate(&ctx->pe1) == cudaSuccess;
@@ -416,6 +419,9 @@ extern "C" int xpngb_create(xpngb_ctx** out, int device) {
     m2_set_attributes();
     if (const char* e = getenv("XPNGB_LAT_MAX_BLOCKS")) ctx->lat_max_blocks = (uint32_t)atol(e);
     if (const char* e = getenv("XPNGB_S16_LAT_MAX_TILES")) ctx->s16_lat_max_tiles = (uint32_t)atol(e);
+    if (const char* e = getenv("XPNGB_DEC_STAGGER1")) ctx->dec_stagger1 = (uint32_t)atol(e);
+    if (const char* e = getenv("XPNGB_DEC_STAGGER2")) ctx->dec_stagger2 = (uint32_t)atol(e);
+    if (const char* e = getenv("XPNGB_DEC_STAGGER_AT")) ctx->dec_stagger_at = (uint32_t)atol(e);
     if (const char* e = getenv("XPNGB_ENC_LAT_MAX_BLOCKS")) ctx->enc_lat_max_blocks = (uint32_t)atol(e);
     if (const char* e = getenv("XPNGB_V2_DIRECT_MAX_TILES")) ctx->v2_direct_max_tiles = (uint32_t)atol(e);
     if (const char* e = getenv("XPNGB_WALK")) { ctx->walk_global = !strcmp(e, "global"); ctx->walk_ring = !strcmp(e, "ring"); }
@@ -1077,6 +1083,7 @@ static int decode_issue(xpngb_ctx* ctx, bool lat, xpngb_image* imgs, uint32_t n,
             auto k_dec_rans_pair_v2_ctx = k_dec_rans_pair<2, 8>;
             LAUNCH_HI(k_dec_rans_pair_v2_ctx, pd_grid(9), PD_WARPS * 32, 0, pd_args(W, PD_S8));
         }
+        if (!ctx->root->dec_stagger_at && !own_stream) CK(cudaEventRecord(ctx->ev_stage, ctx->stream));
         if (launch_walk(1)) return 1;
         BACK_TO_MAIN();
     }
@@ -1135,8 +1142,10 @@ static int decode_issue(xpngb_ctx* ctx, bool lat, xpngb_image* imgs, uint32_t n,
             LAUNCH_HI(k_pd_fill_blocks, (17u * ntiles + 3) / 4, 128, 0, fa);   // run / raw blocks (contexts among them: before the walk)
             LAUNCH_HI(k_dec_rans_pair_v1_s8, pd_grid(11), PD_WARPS * 32, 0, pd_args(W, PD_S8));
         }
+        if (!ctx->root->dec_stagger_at) CK(cudaEventRecord(ctx->ev_stage, ctx->stream));
         if (launch_walk(2)) return 1;
     }
+    if (ctx->root->dec_stagger_at || !(any1 || any2)) CK(cudaEventRecord(ctx->ev_stage, ctx->stream));
     // batches: RGB tiles with word-aligned rows get the row-pitched residual plane and k_dec_unpredict_rgb
     const uint32_t pitched = ((!lat || call_tiles > ctx->root->unr_multi_max_tiles) && !ctx->root->unr_force) ? 1u : 0u;
     bool all_pitched = true;
@@ -1226,6 +1235,9 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
     int rc = 0;
     std::vector<xpngb_ctx*> used(nchunks, nullptr);
     std::vector<uint32_t> cn(nchunks, 0);
+    // staggered waves (batches only): the latency-bound context decode of one wave runs under the issue-bound walk of the wave before
+    uint32_t stagger = lat ? 0u : (l2 ? ctx->dec_stagger2 : ctx->dec_stagger1);
+    if (stagger >= ctx->pipe_lanes) stagger = 0;
     auto chunk_done = [&](uint32_t ci) -> int {   // wait for chunk ci, read its error flag
         xpngb_ctx* lane = used[ci];
         CK(cudaStreamSynchronize(lane->stream));
@@ -1250,6 +1262,7 @@ extern "C" int xpngb_decode(xpngb_ctx* ctx, xpngb_image* imgs, uint32_t n, const
                 snprintf(ctx->err, sizeof ctx->err, "host to device copy failed"); rc = 1; break;
             }
         }
+        if (stagger && ci >= stagger && cudaStreamWaitEvent(lane->stream, used[ci - stagger]->ev_stage, 0) != cudaSuccess) { snprintf(ctx->err, sizeof ctx->err, "cudaStreamWaitEvent failed"); rc = 1; break; }
         rc = decode_issue(lane, lat, imgs + i0, m, hdr.data() + 2 * i0, din, file_offsets + i0, file_sizes + i0, dpx, pixels_cap, (uint32_t)(tiles_est > 0xFFFFFFFFull ? 0xFFFFFFFFu : tiles_est));
         if (!rc && !pixels_on_device) {
             uint64_t lo = ~0ull, hi = 0;
