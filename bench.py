@@ -50,6 +50,48 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def bind_near_gpu(index):
+    """Run this thread (and the threads it starts, and the pinned host memory it allocates: first touch) on the CPUs of the
+    GPU's NUMA node; a host buffer on the far socket costs a third of the PCIe rate.  Returns (record for the JSON line, the
+    affinity to restore before the CPU legs)."""
+    orig = os.sched_getaffinity(0)
+    try:
+        import pynvml as N
+        N.nvmlInit()
+        bus = N.nvmlDeviceGetPciInfo(N.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        dom, rest = bus.split(":", 1)
+        dev = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}"
+        node = int(open(dev + "/numa_node").read())
+        cpus = set()
+        for part in open(dev + "/local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= orig
+        if node >= 0 and cpus and cpus != orig:
+            os.sched_setaffinity(0, cpus)
+            return {"numa_node": node, "cpus": len(cpus), "of": len(orig)}, orig
+        return {"numa_node": node, "cpus": len(orig), "of": len(orig)}, orig
+    except Exception as e:
+        return {"numa_node": None, "note": f"not bound ({type(e).__name__})"}, orig
+
+
+def pcie_probe(torch, dev, h_buf, d_buf, nbytes):
+    """What the box gives between pinned host memory and the GPU: GB/s up, down, and both at once (two streams)."""
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    h2 = torch.empty(nbytes, dtype=torch.uint8).pin_memory(); d2 = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    def run(up, down):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        if up:
+            with torch.cuda.stream(s1): d_buf[:nbytes].copy_(h_buf[:nbytes], non_blocking=True)
+        if down:
+            with torch.cuda.stream(s2): h2.copy_(d2, non_blocking=True)
+        torch.cuda.synchronize(); return time.perf_counter() - t0
+    run(1, 1)
+    up = min(run(1, 0) for _ in range(2)); down = min(run(0, 1) for _ in range(2)); both = min(run(1, 1) for _ in range(2))
+    return {"h2d_GB_s": round(nbytes / 1e9 / up, 1), "d2h_GB_s": round(nbytes / 1e9 / down, 1), "duplex_GB_s": round(2 * nbytes / 1e9 / both, 1)}
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
     Q = "index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -249,6 +291,7 @@ def run_ours(args, rank, world, local_rank):
         _quiet_call(lambda: (dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank)), dist.barrier()))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity, all_cpus = bind_near_gpu(local_rank)          # before any pinned allocation or worker thread
     lib = xpng_b200.lib()
     # A step is a set of JOBS: (level, part of the shard) -> encode, [size/offset gather once the level is encoded], decode.
     # Every job has its own codec context and host thread, so the serial-chain phases of one job overlap the
@@ -410,6 +453,7 @@ def run_ours(args, rank, world, local_rank):
         state["hregion"][lv] = regs
         h_files[lv] = torch.empty(max(base, 16) + 64, dtype=torch.uint8).pin_memory()
     h_back = {lv: torch.empty(max(total, 16) + 64, dtype=torch.uint8).pin_memory() for lv in LEVELS}
+    pcie = pcie_probe(torch, dev, h_px, d_px, min(total, 1 << 30)) if n else None
     e2e_steps = max(1, min(args.steps, 3))
     ms_e2e, calls_e2e = timed(h_px, h_files, h_back, 0, e2e_steps, 1, args.e2e_schedule)
     if n:
@@ -481,7 +525,7 @@ def run_ours(args, rank, world, local_rank):
     achieved = alg_shard / 1e9 / (top_ms / 1e3)
     traffic, traffic_src = None, None
     try:   # DRAM bytes per pixel of that kernel from the committed ncu --set full capture, scaled to this launch
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r03_traffic.json")))
         base = top_name.split(".")[-1]
         for name, rec in tj.items():
             if name == base:
@@ -521,6 +565,9 @@ def run_ours(args, rank, world, local_rank):
     breakdown["latency_4k_frame"] = lat
 
     # ---- the repo's own file API (xpng_store_T / xpng_load_T through tmpfs), like the reference arm does it
+    breakdown["pcie_probe"] = pcie
+    breakdown["host_affinity"] = affinity
+    os.sched_setaffinity(0, all_cpus)                         # the CPU legs below use every host core, like the reference arm
     cpu = None
     if world == 1:
         sample = synth.sintel_batch(range(SEED0, SEED0 + min(F, 16)))
