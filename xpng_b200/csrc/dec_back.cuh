@@ -748,15 +748,20 @@ __global__ void __launch_bounds__(NW * 32) k_dec_unpredict_rows(UnpredArgs A) {
 // for thousands of resident warps (ncu on 4000 tiles: the older kernel issued one instruction per 25 cycles and warp,
 // 58 % of it waiting for shared memory, L1 hit rate 24 % on its word-sized residual loads, 19 warps per SM for its
 // 8.4 KB stage):
-//   * residuals come from the row-pitched plane, FOUR per 128-bit load, twelve steps ahead, into a 16-slot register ring;
+//   * residuals come from the row-pitched plane, FOUR per 128-bit cp.async, twelve steps ahead, into a four-slot ring per lane
+//     in shared memory (2 KB per warp).  Loads into a register ring were tracked by ONE hardware scoreboard (SASS control
+//     bits: every LDG with write barrier 5), so the first use of any slot waited for the load issued a moment before it:
+//     43 % of the kernel's stall samples (ncu r03k); cp.async groups count completions per group instead;
 //   * finished pixels are packed in a 96-bit shift register and leave as three aligned words per four pixels, straight
 //     to global memory (each lane writes its own row; L2 merges the sectors): no staging buffer, no flush loop;
 //   * shared memory per warp is the 2.7 KB boundary row only, so registers (64) bound the residency at 32 warps per SM.
 // Requires word-aligned rows (tile_pitched).  libxpng.c:811-814, :866-897, :911-914.
 // ------------------------------------------------------------------------------------------------
 template <int PM, bool GSUB>
-__device__ __forceinline__ void unpredict_rgb(const UnpredArgs& A, const TileDesc& t, const DecTile* d, uint32_t* brow) {
+__device__ __forceinline__ void unpredict_rgb(const UnpredArgs& A, const TileDesc& t, const DecTile* d, uint32_t* brow, uint4* ring_base) {
     const uint32_t lane = threadIdx.x & 31;
+    uint4* ring = ring_base + lane;                                   // [slot][lane]
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
     const uint8_t* blob = A.in + d->blob_off;
     const uint32_t w = t.w, pitch = (w + 3u) & ~3u;
     const uint32_t* res = A.resv + resv_base(t);
@@ -779,22 +784,17 @@ __device__ __forceinline__ void unpredict_rgb(const UnpredArgs& A, const TileDes
         uint8_t* orow = dst + (uint64_t)y * t.bpr;                    // word aligned
         uint32_t left = 0, uprev = 0, a0 = 0, a1 = 0, a2 = 0;
         uint32_t hist[SKEW] = { 0, 0, 0, 0 };
-        uint32_t rn[RING];
+        // the lane's column group cg (columns 4cg .. 4cg + 3) lives in slot (cg + lane) % 4, i.e. slot (j / 4) % 4 at step j of the
+        // unrolled loop for every lane; one cp.async group per four steps, three groups in flight
+        asm volatile("cp.async.wait_all;" ::: "memory");
 #pragma unroll
-        for (int k = 0; k < RING; k++) rn[k] = 0;
-        if (rowok) {   // columns 0 .. 11: column c is consumed at step c + 4 * lane, i.e. from slot (c + 4 * lane) % RING
-#pragma unroll
-            for (int g = 0; g < AHEAD / 4; g++) {
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if (4u * g < pitch) v = __ldg(reinterpret_cast<const uint4*>(rrow) + g);
-                const uint32_t vv[4] = { v.x, v.y, v.z, v.w };
-                const uint32_t sb = (4u * g + SKEW * lane) % RING;   // a multiple of 4
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-#pragma unroll
-                    for (int k = 0; k < RING / 4; k++) rn[4 * k + q] = sb == (uint32_t)(4 * k) ? vv[q] : rn[4 * k + q];
-            }
+        for (int g = 0; g < AHEAD / 4; g++) {   // columns 0 .. 11
+            const uint32_t go = (rowok && 4u * g < pitch) ? 1u : 0u;
+            asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q cp.async.cg.shared.global [%0], [%1], 16;\n}"
+                         :: "r"(ring_s + (((uint32_t)g + lane) & 3u) * 512u), "l"(rrow + 4 * g), "r"(go) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
         }
+        uint4 r4 = make_uint4(0, 0, 0, 0);
         const uint32_t steps = (w + SKEW * 31 + RING - 1) / RING * RING;
         for (uint32_t s0 = 0; s0 < steps; s0 += RING) {
 #pragma unroll
@@ -805,13 +805,15 @@ __device__ __forceinline__ void unpredict_rgb(const UnpredArgs& A, const TileDes
                 const uint32_t ub = brow[min(s, w - 1)];              // row above the band (band 0 never uses it)
                 uint32_t U = __shfl_up_sync(0xffffffffu, hist[j % SKEW], 1);   // the upper lane's pixel of four steps ago: column x
                 U = lane == 0 ? ub : U;
-                const uint32_t rv = rn[j];
-                if (j % 4 == 0) {   // the four residuals of columns x + 12 .. x + 15 go to the slots consumed last
+                if (j % 4 == 0) {   // my four residuals of columns x .. x + 3 have landed; request columns x + 12 .. x + 15
+                    asm volatile("cp.async.wait_group 2;" ::: "memory");
+                    r4 = ring[((j / 4) % 4) * 32];
                     const uint32_t go = (act && x + AHEAD < pitch) ? 1u : 0u;
-                    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %5, 0;\n @q ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n}"
-                                 : "+r"(rn[(j + 12) % RING]), "+r"(rn[(j + 13) % RING]), "+r"(rn[(j + 14) % RING]), "+r"(rn[(j + 15) % RING])
-                                 : "l"(rrow + x + AHEAD), "r"(go));
+                    asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q cp.async.cg.shared.global [%0], [%1], 16;\n}"
+                                 :: "r"(ring_s + ((j / 4 + 3) % 4) * 512u), "l"(rrow + x + AHEAD), "r"(go) : "memory");
+                    asm volatile("cp.async.commit_group;" ::: "memory");
                 }
+                const uint32_t rv = j % 4 == 0 ? r4.x : (j % 4 == 1 ? r4.y : (j % 4 == 2 ? r4.z : r4.w));
                 uint32_t pix = 0;
                 if (act) {
                     uint32_t r = swar_unzz(rv);
@@ -847,6 +849,7 @@ __device__ __forceinline__ void unpredict_rgb(const UnpredArgs& A, const TileDes
 
 __global__ void __launch_bounds__(32) k_dec_unpredict_rgb(UnpredArgs A) {
     __shared__ uint32_t brow[UNR_MAXW];
+    __shared__ uint4 rring[4][32];                     // residual ring: four column groups per lane
     const uint32_t tile = blockIdx.x;
     const TileDesc t = A.tiles[tile];
     const uint32_t mode = A.imgs[t.img].mode;
@@ -857,10 +860,10 @@ __global__ void __launch_bounds__(32) k_dec_unpredict_rgb(UnpredArgs A) {
     const bool grey = (d->m >> 4) == 2;
     const uint32_t pm = grey ? (d->m & 3u) : (((d->m >> 1) & 1u) ? 3u : 2u);
     const bool G = !grey && (d->m & 1u);
-    if (pm == 3) { if (G) unpredict_rgb<3, true>(A, t, d, brow); else unpredict_rgb<3, false>(A, t, d, brow); }
-    else if (pm == 2) { if (G) unpredict_rgb<2, true>(A, t, d, brow); else unpredict_rgb<2, false>(A, t, d, brow); }
-    else if (pm == 1) unpredict_rgb<1, false>(A, t, d, brow);
-    else unpredict_rgb<0, false>(A, t, d, brow);
+    if (pm == 3) { if (G) unpredict_rgb<3, true>(A, t, d, brow, &rring[0][0]); else unpredict_rgb<3, false>(A, t, d, brow, &rring[0][0]); }
+    else if (pm == 2) { if (G) unpredict_rgb<2, true>(A, t, d, brow, &rring[0][0]); else unpredict_rgb<2, false>(A, t, d, brow, &rring[0][0]); }
+    else if (pm == 1) unpredict_rgb<1, false>(A, t, d, brow, &rring[0][0]);
+    else unpredict_rgb<0, false>(A, t, d, brow, &rring[0][0]);
 }
 
 // Raw grey plane (level 2, m = 0x28, libxpng.c:875-879)
