@@ -67,22 +67,16 @@ __device__ __forceinline__ uint32_t pair_chain(const uint4* EA, const uint2* EB,
         const uint32_t bits = pend_bal >> bsh;                    // no POPC here: its ~20-cycle latency would stall the in-order pipe every step
         wcount += (bits & 1u) + ((bits >> 1) & 1u);
     };
-    // symbols reach the chain through a four-slot ring per lane in shared memory, filled by cp.async three groups (24 steps)
-    // ahead: no register ever waits for global memory (a register rotation v <- vnext <- vnext2 <- load makes the move of
-    // the youngest value wait for a load issued only one group earlier: 20 % of the stall samples of the kernel, ncu r02z)
-    __shared__ uint4 s_sym[4][32];
-    const uint32_t sring = (uint32_t)__cvta_generic_to_shared(&s_sym[0][lane]);
-    auto prefetch = [&](const uint32_t g) {
-        if (g < G) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sring + (g & 3u) * 512u), "l"(in16 + (VER == 2 ? g : G - 1 - g)) : "memory");
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    prefetch(0); prefetch(1); prefetch(2);
+    // symbols are fetched two groups (16 steps, > 1500 cycles) ahead: the load never stalls the in-order pipe
+    uint4 vnext = make_uint4(0, 0, 0, 0), vnext2 = make_uint4(0, 0, 0, 0);
+    if (G) vnext = in16[VER == 2 ? 0 : G - 1];
+    if (G > 1) vnext2 = in16[VER == 2 ? 1 : G - 2];
     for (uint32_t g = 0; g < Gmax; g++) {
         const bool gv = g < G;
         const uint32_t gi = gv ? (VER == 2 ? g : G - 1 - g) : 0u;
-        asm volatile("cp.async.wait_group 2;" ::: "memory");
-        const uint4 v = s_sym[g & 3u][lane];
-        prefetch(g + 3);                                              // into the slot read one group ago
+        uint4 v = vnext;
+        vnext = vnext2;
+        if (g + 2 < G) vnext2 = in16[VER == 2 ? g + 2 : G - 3 - g];
         const uint32_t nvalid = gv ? min(16u, nn - 16u * gi) : 0u;     // symbols of this group inside the stream
         const bool partial = nvalid < 16u;
         uint32_t vmask = 0xFFFFu;                                    // bit k: symbol k of the group is real
