@@ -171,9 +171,10 @@ def _tmpdir():
     return "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
 
 
-def file_api_steps(L, frames, steps, warmup, tag):
+def file_api_steps(L, frames, steps, warmup, tag, callers=1):
     """K steps of the file-at-a-time API (xpng_store_T / xpng_load_T, T = 0) over `frames` at levels 1 and 2, files on tmpfs.
     `L` is a CDLL exporting the reference's entry points (the reference itself or this repo's drop-in).
+    callers > 1: the frames of a level are handed to that many host threads (the API is re-entrant; one frame per call either way).
     Returns (seconds per step, {call: seconds per step})."""
     L.xpng_store_T.restype = C.c_bool
     L.xpng_store_T.argtypes = [C.c_uint64, C.c_uint64, C.POINTER(_Xpng), C.c_char_p]
@@ -185,16 +186,25 @@ def file_api_steps(L, frames, steps, warmup, tag):
     paths = [os.path.join(_tmpdir(), f"_xpng_{tag}_{os.getpid()}_{i}.xpng").encode() for i in range(len(frames))]
     per_call = {}
 
+    tp = ThreadPoolExecutor(callers) if callers > 1 else None
+    each = (lambda fn, items: list(tp.map(fn, items))) if tp else (lambda fn, items: [fn(it) for it in items])
+
+    def store(lv):
+        def one(k):
+            assert not L.xpng_store_T(0, lv, C.byref(pms[k]), paths[k])
+        return one
+
+    def load(k):
+        out = _Xpng()
+        assert not L.xpng_load_T(0, paths[k], C.byref(out))
+        libc.free(C.c_void_p(out.p))
+
     def step(rec):
         for lv in LEVELS:
             t0 = time.perf_counter()
-            for pm, p in zip(pms, paths):
-                assert not L.xpng_store_T(0, lv, C.byref(pm), p)
+            each(store(lv), range(len(pms)))
             t1 = time.perf_counter()
-            for p in paths:
-                out = _Xpng()
-                assert not L.xpng_load_T(0, p, C.byref(out))
-                libc.free(C.c_void_p(out.p))
+            each(load, range(len(pms)))
             t2 = time.perf_counter()
             if rec:
                 per_call[f"enc{lv}"] = per_call.get(f"enc{lv}", 0.0) + (t1 - t0)
@@ -207,6 +217,8 @@ def file_api_steps(L, frames, steps, warmup, tag):
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     finally:
+        if tp:
+            tp.shutdown()
         for p in paths:
             if os.path.exists(p):
                 os.remove(p)
@@ -575,6 +587,13 @@ def run_ours(args, rank, world, local_rank):
         breakdown["e2e_file"] = {"MPix_s": round(4 * len(sample) * npx_frame / 1e6 / per_step, 1), "frames": len(sample),
                                  "how": "this library's xpng_store_T/xpng_load_T, one frame per call, files on tmpfs (the reference arm's own method)",
                                  "calls": call_table(calls, len(sample) * npx_frame)}
+        try:    # the same calls from eight host threads at once: what a multi-threaded caller of the re-entrant API sees
+            per_step8, calls8 = file_api_steps(C.CDLL(xpng_b200.lib_path()), sample, 2, 1, "ours8", callers=8)
+            breakdown["e2e_file_8_callers"] = {"MPix_s": round(4 * len(sample) * npx_frame / 1e6 / per_step8, 1), "frames": len(sample),
+                                               "how": "as e2e_file, the frames of a level handed to 8 host threads (one frame per call, contexts from the library's pool)",
+                                               "calls": call_table(calls8, len(sample) * npx_frame)}
+        except Exception as e:
+            breakdown["e2e_file_8_callers"] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
         if not args.no_cpu_baseline:
             nref = min(F, 32)
             ref_frames = synth.sintel_batch(range(SEED0, SEED0 + nref))
